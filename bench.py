@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the VFGS hardware-layer hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+
+One "step" is one pass of the hot path over one batch of synthetic frames of the workload's size
+(default: the BASELINE.json headline, 3840x2160 10-bit 4:2:0). The batch is a pool of distinct
+frames several GB large, so every step streams from and to HBM (inputs larger than L2).
+
+  value      frames/s, device-resident (inputs already in HBM), CUDA events on the launching stream,
+             max over ranks; whole job over all N GPUs
+  e2e        same metric through the host entry point of the C-ABI (pinned host buffers; H2D, kernels
+             and D2H inside the timed region)
+  roofline   grain kernel alone: algorithmic bytes (samples x (bytes in + bytes out)) / its average
+             launch duration (CUDA events around each launch), against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the reference's own CPU implementation (oracle/_ref, unmodified sources compiled with
+             gcc -O3 -mavx2) on this host's cores, on a bounded sample of the same workload
+  --impl reference  times that CPU implementation instead of the CUDA path (rank 0 only)
+
+Multi-GPU: one process per GPU (torchrun). Frames are sharded: every rank owns a contiguous run of
+each step's global batch and derives its LFSR start state by jump-ahead; there is no collective on
+the data path (NCCL is used only for the barrier and the max-over-ranks of the timings).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "4k_10bit_420_frames_per_sec_device_resident"
+UNIT = "frames/s"
+
+# name -> (golden case, width, height, fmt, depth, out_depth)
+WORKLOADS = {
+    "4k420_afgs1_10to10": ("fgs_afgs1_test1.cfg|d10|420|g100", 3840, 2160, "420", 10, 0),
+    "4k420_afgs1_10to8": ("fgs_afgs1_test1.cfg|d10|420|g100", 3840, 2160, "420", 10, 8),
+    "4k420_sei_default": ("fgs_sei.cfg|d10|420|g100", 3840, 2160, "420", 10, 0),
+    "4k420_ff_test5": ("fgs_sei_ff_test5.cfg|d10|420|g100", 3840, 2160, "420", 10, 0),
+    "1080p420_ff_test1": ("fgs_sei_ff_test1.cfg|d10|420|g100", 1920, 1080, "420", 10, 0),
+    "1080p420_ar_test1": ("fgs_sei_ar_test1.cfg|d10|420|g100", 1920, 1080, "420", 10, 0),
+    "4k422_ff_test4_gain150": ("fgs_sei_ff_test4.cfg|d10|422|g150", 3840, 2160, "422", 10, 0),
+    "4k444_ff_test4_gain150": ("fgs_sei_ff_test4.cfg|d10|444|g150", 3840, 2160, "444", 10, 0),
+    "8k420_ff_test1": ("fgs_sei_ff_test1.cfg|d10|420|g100", 7680, 4320, "420", 10, 0),
+}
+DEFAULT_WORKLOAD = "4k420_afgs1_10to10"
+POOL_INPUT_BYTES = 6.4e9  # per GPU; x2 with the output pool, far above the 126 MB L2
+
+
+def frame_geometry(w, h, fmt, depth, out_depth):
+    sx, sy = {"420": (2, 2), "422": (2, 1), "444": (1, 1)}[fmt]
+    samples = w * h + 2 * (w // sx) * (h // sy)
+    isz = 2 if depth > 8 else 1
+    osz = 2 if (out_depth or depth) > 8 else 1
+    return samples, samples * isz, samples * osz
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Polls SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
+    NOTE = {"sw_power_cap": 0x4}
+
+    def __init__(self, index: int, period_s: float = 0.004):
+        super().__init__(daemon=True)
+        self.index, self.period, self.stop_flag = index, period_s, threading.Event()
+        self.sm, self.reasons, self.max_mhz, self.err = [], 0, None, None
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while not self.stop_flag.is_set():
+                self.sm.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                try:
+                    self.reasons |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    self.reasons |= int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                time.sleep(self.period)
+        except Exception as e:  # NVML missing: report it, do not invent numbers
+            self.err = repr(e)
+
+    def result(self):
+        self.stop_flag.set()
+        self.join(timeout=2)
+        names = [n for n, bit in {**self.BAD, **self.NOTE}.items() if self.reasons & bit]
+        out = {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+               "reasons": names, "samples": len(self.sm)}
+        if self.err:
+            out["error"] = self.err
+        return out
+
+
+# ------------------------------------------------------------------------------------- CPU arm
+_W = {}
+
+
+def _cpu_worker_init(case, w, h, fmt, depth, out_depth, frames_per_worker, use_ref):
+    from oracle import pyoracle
+    from tests.util import load_golden, program_case
+    G = load_golden()
+    hw = pyoracle.Reference() if use_ref else pyoracle.Oracle()
+    st = G.state(case)
+    pyoracle.program_hw_from_state(hw, st)
+    rng = np.random.default_rng(os.getpid())
+    samples, _, _ = frame_geometry(w, h, fmt, depth, out_depth)
+    maxv = (1 << depth) - 1
+    data = rng.integers(0, maxv + 1, size=frames_per_worker * samples, dtype=np.uint16 if depth > 8 else np.uint8)
+    _W.update(hw=hw, st=st, data=data, work=data.copy(), n=frames_per_worker, w=w, h=h, fmt=fmt, depth=depth,
+              od=out_depth, use_ref=use_ref, out8=np.empty(data.size, dtype=np.uint8))
+
+
+def _cpu_worker_step(_):
+    from oracle import pyoracle
+    from oracle.pyoracle import _ptr
+    W = _W
+    np.copyto(W["work"], W["data"])
+    _, _, cw, ch = pyoracle.frame_samples(W["w"], W["h"], W["fmt"])
+    t0 = time.perf_counter()
+    if W["use_ref"]:
+        # the reference's own line walk (vfgs_main.c:664-682 -> vfgs_hw.c:288) and yuv_to_8bit
+        W["hw"].L.refh_add_grain_frames_packed(_ptr(W["work"]), W["n"], W["w"], W["h"], cw, ch, W["depth"])
+        if W["od"] == 8 and W["depth"] == 10:
+            W["hw"].L.refh_to_8bit_packed(_ptr(W["out8"]), _ptr(W["work"]), W["n"], W["w"], W["h"], cw, ch)
+    else:
+        W["hw"].add_grain_frames(W["work"], W["n"], W["w"], W["h"], W["od"])
+    return time.perf_counter() - t0
+
+
+class CpuArm:
+    """The reference CPU implementation on all host cores: one forked process per core (the reference
+    keeps its state in file-scope statics and is single-threaded), each on its own frames."""
+
+    def __init__(self, workload, frames_per_worker):
+        import multiprocessing as mp
+        from oracle import pyoracle
+        pyoracle.build()
+        self.use_ref = pyoracle.have_reference()
+        try:
+            self.cores = len(os.sched_getaffinity(0))
+        except Exception:
+            self.cores = os.cpu_count() or 1
+        case, w, h, fmt, depth, od = WORKLOADS[workload]
+        self.fpw = frames_per_worker
+        self.pool = mp.get_context("fork").Pool(self.cores, _cpu_worker_init, (case, w, h, fmt, depth, od, frames_per_worker, self.use_ref))
+
+    def step(self):
+        t0 = time.perf_counter()
+        self.pool.map(_cpu_worker_step, range(self.cores), chunksize=1)
+        return time.perf_counter() - t0
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+    @property
+    def kind(self):
+        return "reference" if self.use_ref else "port"
+
+    def describe(self):
+        what = "oracle/_ref (unmodified reference, gcc -O3 -mavx2, asserts on)" if self.use_ref else "oracle port (oracle/vfgs_oracle.c)"
+        return f"{what}; {self.cores} forked workers x {self.fpw} frames per step, in-memory frames, file I/O excluded"
+
+
+def cpu_frames_per_worker(w, h):
+    return max(1, int(round(6 * (3840 * 2160) / (w * h))))  # ~0.5 s of work per worker per step
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    case, w, h, fmt, depth, od = WORKLOADS[args.workload]
+    fpw = cpu_frames_per_worker(w, h)
+    arm = CpuArm(args.workload, fpw)
+    for _ in range(args.warmup):
+        arm.step()
+    t = [arm.step() for _ in range(args.steps)]
+    arm.close()
+    total = sum(t)
+    frames = arm.cores * fpw * args.steps
+    value = frames / total
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32", "data": "synthetic", "impl": "reference",
+        "config": workload_config(args.workload, arm.cores * fpw, "cpu: frames stay in host memory"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": arm.describe()},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(name, frames_per_step, l2_note):
+    case, w, h, fmt, depth, od = WORKLOADS[name]
+    return {"workload": f"{w}x{h} {depth}-bit {fmt[0]}:{fmt[1]}:{fmt[2]} -> {od or depth}-bit, grain config {case.split('|')[0]}"
+                        f"{' gain ' + case.split('|g')[1] if not case.endswith('g100') else ''}, uniform random samples",
+            "name": name, "frames_per_step": frames_per_step, "l2": l2_note}
+
+
+# ------------------------------------------------------------------------------------- CUDA arm
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world == 1:
+        # not under torchrun: re-launch ourselves the way the driver does
+        import subprocess
+        port = 29500 + (os.getpid() % 2000)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    case, w, h, fmt, depth, od = WORKLOADS[args.workload]
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # timed first, before this process creates a CUDA context (the workers are forked)
+        fpw = cpu_frames_per_worker(w, h)
+        arm = CpuArm(args.workload, fpw)
+        arm.step()
+        tt = [arm.step() for _ in range(3)]
+        arm.close()
+        cpu_baseline = {"value": arm.cores * fpw * len(tt) / sum(tt), "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
+                        "sample": arm.describe() + f"; {len(tt)} timed steps after 1 warm-up"}
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from tests.util import Oracle, load_golden, program_case, synth_frames
+    from versatilefilmgrain_b200 import VfgsHw
+    from versatilefilmgrain_b200.sharding import position_shard
+
+    case, w, h, fmt, depth, od = WORKLOADS[args.workload]
+    samples, in_bytes, out_bytes = frame_geometry(w, h, fmt, depth, od)
+    G = load_golden()
+    hw = VfgsHw(device=local)
+    hw.reset()
+    st = program_case(hw, G, case)
+    epoch = [int(v) for v in st["lfsr"]]
+
+    # parity gate: a strip of the workload's width against the oracle
+    strip_h, strip_n = 72, 2
+    strip = synth_frames(strip_n, w, strip_h, fmt, depth, seed=3)
+    d_s = torch.from_numpy(strip.view(np.int16) if depth > 8 else strip).cuda()
+    d_o = torch.zeros(strip.size, dtype=torch.int16 if (od or depth) > 8 else torch.uint8, device="cuda")
+    hw.add_grain_frames_device(d_s, d_o, strip_n, w, strip_h, od)
+    torch.cuda.synchronize()
+    got = d_o.cpu().numpy()
+    got = got.view(np.uint16) if (od or depth) > 8 else got
+    orc = Oracle(); program_case(orc, G, case)
+    if not np.array_equal(got, orc.add_grain_frames(strip, strip_n, w, strip_h, od)):
+        print(json.dumps({"error": "parity gate failed: CUDA output differs from the oracle", "workload": args.workload}), flush=True)
+        return 2
+    del d_s, d_o
+
+    # resident pool of distinct frames (uniform random codes: worst case for the LUT/pattern gathers)
+    F = args.frames_per_step or int(max(8, min(1024, POOL_INPUT_BYTES // in_bytes)))
+    gen = torch.Generator(device="cuda"); gen.manual_seed(1234 + rank)
+    if depth > 8:
+        src = torch.randint(0, 1 << depth, (F * samples,), dtype=torch.int16, device="cuda", generator=gen)
+    else:
+        src = torch.randint(0, 256, (F * samples,), dtype=torch.uint8, device="cuda", generator=gen)
+    dst = torch.empty(F * samples, dtype=torch.int16 if (od or depth) > 8 else torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream()
+
+    def step(s):
+        # rank r owns frames [r*F, (r+1)*F) of step s's global batch of world*F frames
+        position_shard(hw, epoch, (s * world + rank) * F, w, h)
+        hw.add_grain_frames_device(src, dst, F, w, h, od, stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for s in range(args.warmup):
+        step(s)
+    barrier()
+    sampler = ClockSampler(local); sampler.start()
+    hw.kernel_timing(True)
+    launches0 = hw.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for s in range(args.steps):
+        step(args.warmup + s)
+    e1.record(stream)
+    barrier()
+    clocks = sampler.result()
+    ms = e0.elapsed_time(e1)
+    k_ms, k_n = hw.kernel_time()
+    hw.kernel_timing(False)
+    gpu_launches = hw.launch_count() - launches0
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * F * args.steps / (ms_max * 1e-3)
+
+    # end to end through the host entry point: pinned host buffers, H2D + kernels + D2H timed
+    Fe = args.e2e_frames or int(max(4, min(64, 4e8 // in_bytes)))
+    h_in = torch.empty(Fe * samples, dtype=src.dtype).pin_memory()
+    h_in.copy_(src[: Fe * samples])
+    h_out = torch.empty(Fe * samples, dtype=dst.dtype).pin_memory()
+    del src, dst
+    torch.cuda.empty_cache()
+    e2e_steps = max(3, min(args.steps, 10))
+    for s in range(2):
+        hw.add_grain_frames_host(h_in, h_out, Fe, w, h, od)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(e2e_steps):
+        hw.add_grain_frames_host(h_in, h_out, Fe, w, h, od)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * Fe * e2e_steps / float(t.item())
+
+    peak, peak_src = measured_peak_gbs()
+    algo_bytes = F * (in_bytes + out_bytes)
+    achieved = algo_bytes / (k_ms / max(k_n, 1) * 1e-3) / 1e9 if k_n else None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32", "data": "synthetic",
+        "config": workload_config(args.workload, F, f"inputs larger than L2: resident pool {F * (in_bytes + out_bytes) / 1e9:.1f} GB per GPU streamed once per step"),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": Fe * in_bytes, "d2h_bytes_per_step": Fe * out_bytes,
+                "frames_per_step": Fe, "steps": e2e_steps, "host_buffers": "pinned"},
+        "gpu_launches": int(gpu_launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                     "kernel": "fgs_apply_kernel", "bytes_per_launch": algo_bytes, "avg_launch_ms": (k_ms / k_n) if k_n else None,
+                     "kernel_share_of_step": (k_ms / ms) if ms else None,
+                     "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None},
+        "bytes_per_frame": in_bytes + out_bytes,
+        "device_resident_gbs": value * (in_bytes + out_bytes) / 1e9,
+        "parity": "strip checked bit-exact against oracle before timing",
+    }
+
+    if cpu_baseline is not None:
+        line["cpu_baseline"] = cpu_baseline
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--frames-per-step", type=int, default=0)
+    ap.add_argument("--e2e-frames", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
+    sys.exit(run_reference_arm(args) if args.impl == "reference" else run_b200_arm(args))
+
+
+if __name__ == "__main__":
+    main()

@@ -185,6 +185,20 @@ class Oracle:
         r = (C.c_uint32 * 4)(*regs)
         self.L.oracle_set_lfsr(self.h, r)
 
+    def skip_frames(self, n, width, height):
+        """Registers after n whole frames without processing them (test helper mirroring
+        vfgs_b200_skip_frames): n * (R - 1) * nb steps, see oracle_add_grain_frames."""
+        nb, rows = (width + 15) // 16, (height + 15) // 16
+        r = self.get_lfsr()
+        s0, adv = r[2], n * (rows - 1) * nb
+        if n > 0:
+            if rows >= 2:
+                r[3] = self.lfsr_jump(s0, adv - nb)
+                r[2] = self.lfsr_jump(s0, adv)
+            r[0] = self.lfsr_jump(r[2], nb)
+            r[1] = self.lfsr_jump(r[3], nb)
+            self.set_lfsr(r)
+
     def state(self) -> dict:
         s = RefState()
         self.L.oracle_get_state(self.h, C.byref(s))
@@ -305,8 +319,9 @@ def synth_frames(nframes, width, height, fmt="420", depth=10, seed=1, kind="unif
     ys, cs, _, _ = frame_samples(width, height, fmt)
     n = nframes * (ys + 2 * cs)
     idx = np.arange(n, dtype=np.uint64)
-    x = (idx + np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15)) & np.uint64(0xFFFFFFFFFFFFFFFF)
+    salt = np.uint64((int(seed) * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF)
     with np.errstate(over="ignore"):
+        x = idx + salt
         x ^= x >> np.uint64(30); x *= np.uint64(0xBF58476D1CE4E5B9)
         x ^= x >> np.uint64(27); x *= np.uint64(0x94D049BB133111EB)
         x ^= x >> np.uint64(31)

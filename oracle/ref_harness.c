@@ -132,8 +132,30 @@ REFH_API void refh_add_grain_frames_packed(void* buf, int nframes, int w, int h,
 	int sz = bitdepth > 8 ? 2 : 1;
 	size_t ysz = (size_t)w * h * sz, csz = (size_t)cw * ch * sz;
 	unsigned char* p = buf;
-	for (int f = 0; f < nframes; f++, p += ysz + 2 * csz)
-		refh_add_grain_frame(p, p + ysz, p + ysz + csz, w, h, w, cw, bitdepth, h == ch);
+	if ((w & 15) == 0 && (cw & 7) == 0 && (h == ch || (h & 1) == 0)) {
+		for (int f = 0; f < nframes; f++, p += ysz + 2 * csz)
+			refh_add_grain_frame(p, p + ysz, p + ysz + csz, w, h, w, cw, bitdepth, h == ch);
+		return;
+	}
+	/* The hw layer always works on whole 16-sample blocks (vfgs_hw.c:301), so a picture whose
+	 * width is not a multiple of 16 needs the stride padding yuv_alloc gives it (yuv.c:65,74:
+	 * strides rounded up to 64 samples, heights to 16 lines); the padding is zeroed here. */
+	int stride = (w + 63) & ~63, cstride = (cw + 63) & ~63;
+	size_t ypad = (size_t)stride * (h + 16) * sz, cpad = (size_t)cstride * (ch + 16) * sz;
+	unsigned char* tmp = calloc(1, ypad + 2 * cpad);
+	for (int f = 0; f < nframes; f++, p += ysz + 2 * csz) {
+		unsigned char* src[3] = { p, p + ysz, p + ysz + csz };
+		unsigned char* dst[3] = { tmp, tmp + ypad, tmp + ypad + cpad };
+		memset(tmp, 0, ypad + 2 * cpad);
+		for (int c = 0; c < 3; c++)
+			for (int y = 0; y < (c ? ch : h); y++)
+				memcpy(dst[c] + (size_t)y * (c ? cstride : stride) * sz, src[c] + (size_t)y * (c ? cw : w) * sz, (size_t)(c ? cw : w) * sz);
+		refh_add_grain_frame(dst[0], dst[1], dst[2], w, h, stride, cstride, bitdepth, h == ch);
+		for (int c = 0; c < 3; c++)
+			for (int y = 0; y < (c ? ch : h); y++)
+				memcpy(src[c] + (size_t)y * (c ? cw : w) * sz, dst[c] + (size_t)y * (c ? cstride : stride) * sz, (size_t)(c ? cw : w) * sz);
+	}
+	free(tmp);
 }
 
 /* yuv.c:216-258 through its own entry point, on tightly packed planes. */

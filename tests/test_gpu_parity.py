@@ -1,0 +1,272 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI (ctypes), against the oracle on the
+same seeded inputs, and against the digests the unmodified reference produced (tests/golden).
+Bit-exact: every comparison is array equality on integer samples. Run with -m gpu on a B200."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from tests.util import (Oracle, first_mismatch, load_golden, parse_output_key, program_case, sha,
+                        synth_frames)
+
+pytestmark = pytest.mark.gpu
+
+G = load_golden()
+CASES = G.runnable()
+
+
+@pytest.fixture(scope="module")
+def hw():
+    import torch
+    assert torch.cuda.is_available(), "these tests need a CUDA device"
+    from versatilefilmgrain_b200 import VfgsHw
+    h = VfgsHw(device=0)
+    return h
+
+
+def to_dev(a: np.ndarray):
+    import torch
+    t = torch.from_numpy(a.view(np.int16) if a.dtype == np.uint16 else a)
+    return t.cuda()
+
+
+def from_dev(t, dtype):
+    a = t.cpu().numpy()
+    return a.view(np.uint16) if dtype == np.uint16 else a
+
+
+def run_device(hw, frames, n, w, h, od, depth, inplace=False):
+    import torch
+    src = to_dev(frames)
+    if inplace:
+        dst = src
+    else:
+        dst = torch.zeros(frames.size, dtype=torch.uint8 if (od == 8 or depth == 8) else torch.int16, device="cuda")
+    hw.add_grain_frames_device(src, dst, n, w, h, od)
+    torch.cuda.synchronize()
+    return from_dev(dst, np.uint8 if (od == 8 or depth == 8) else np.uint16)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_every_golden_case(hw, case):
+    """All cfg/ files x depth/format/gain variants: CUDA == oracle == reference digest, LFSR
+    registers afterwards == the reference's."""
+    meta = G.cases[case]
+    for key, want in meta["outputs"].items():
+        w, h, n, iseed, od = parse_output_key(key)
+        hw.reset()
+        program_case(hw, G, case)
+        frames = synth_frames(n, w, h, meta["fmt"], meta["depth"], seed=iseed)
+        got = run_device(hw, frames, n, w, h, od, meta["depth"])
+        o = Oracle(); program_case(o, G, case)
+        exp = o.add_grain_frames(frames, n, w, h, od)
+        assert np.array_equal(got, exp), (case, key, first_mismatch(got, exp, w, h, meta["fmt"], n))
+        assert sha(got) == want["sha256"], (case, key)
+        assert hw.get_lfsr() == want["lfsr_after"], (case, key)
+
+
+@pytest.mark.parametrize("case", ["fgs_afgs1_test1.cfg|d10|420|g100", "fgs_sei_ff_test1.cfg|d8|420|g100",
+                                  "fgs_sei_ff_test4.cfg|d10|444|g150"])
+def test_in_place(hw, case):
+    meta = G.cases[case]
+    w, h, n = 384, 88, 2
+    frames = synth_frames(n, w, h, meta["fmt"], meta["depth"], seed=2)
+    hw.reset(); program_case(hw, G, case)
+    got = run_device(hw, frames, n, w, h, 0, meta["depth"], inplace=True)
+    o = Oracle(); program_case(o, G, case)
+    assert np.array_equal(got, o.add_grain_frames(frames, n, w, h, 0))
+
+
+def test_in_place_refused_when_pattern_depends_on_sample(hw):
+    import torch
+    from versatilefilmgrain_b200 import VfgsError
+    hw.reset(); program_case(hw, G, "fgs_sei.cfg|d10|420|g100")  # 8 luma patterns
+    buf = torch.zeros(256 * 144 * 3 // 2, dtype=torch.int16, device="cuda")
+    with pytest.raises(VfgsError):
+        hw.add_grain_frames_device(buf, buf, 1, 256, 144, 0)
+
+
+@pytest.mark.parametrize("case,od", [("fgs_sei_ff_test5.cfg|d10|420|g100", 0), ("fgs_afgs1_test1.cfg|d10|420|g100", 8),
+                                      ("fgs_sei.cfg|d8|420|g100", 0)])
+def test_host_pipeline_many_chunks(hw, case, od):
+    """Host entry point: enough frames for several chunks to be in flight on the three streams."""
+    meta = G.cases[case]
+    w, h, n = 1920, 1080, 45
+    frames = synth_frames(n, w, h, "420", meta["depth"], seed=6)
+    out = np.zeros(frames.size, dtype=np.uint8 if (od == 8 or meta["depth"] == 8) else np.uint16)
+    hw.reset(); program_case(hw, G, case)
+    hw.add_grain_frames_host(frames, out, n, w, h, od)
+    o = Oracle(); program_case(o, G, case)
+    exp = o.add_grain_frames(frames, n, w, h, od)
+    assert np.array_equal(out, exp), first_mismatch(out, exp, w, h, "420", n)
+    assert hw.get_lfsr() == o.get_lfsr()
+
+
+def test_host_pipeline_pinned_in_place(hw):
+    import torch
+    case = "fgs_sei_ff_test7.cfg|d10|420|g100"
+    w, h, n = 1280, 720, 40
+    frames = synth_frames(n, w, h, "420", 10, seed=9)
+    pinned = torch.from_numpy(frames.view(np.int16)).pin_memory()
+    hw.reset(); program_case(hw, G, case)
+    hw.add_grain_frames_host(pinned, pinned, n, w, h, 0)
+    o = Oracle(); program_case(o, G, case)
+    assert np.array_equal(pinned.numpy().view(np.uint16), o.add_grain_frames(frames, n, w, h, 0))
+
+
+@pytest.mark.parametrize("case", ["fgs_sei.cfg|d10|420|g100", "fgs_afgs1_test3.cfg|d8|420|g100",
+                                  "fgs_sei_ff_test4.cfg|d10|422|g150"])
+def test_line_entry_point(hw, case):
+    """vfgs_add_grain_line, driven like vfgs_main.c:664-682, then a frame call, then lines again:
+    the two entry points share one register state and interleave bit-exactly."""
+    meta = G.cases[case]
+    fmt, depth = meta["fmt"], meta["depth"]
+    sx, sy = {"420": (2, 2), "422": (2, 1), "444": (1, 1)}[fmt]
+    w, h = 272, 56
+    cw, ch = w // sx, h // sy
+    frames = synth_frames(3, w, h, fmt, depth, seed=13)
+    o = Oracle(); program_case(o, G, case)
+    exp = o.add_grain_frames(frames, 3, w, h, 0)
+    hw.reset(); program_case(hw, G, case)
+    work = frames.copy()
+    per = w * h + 2 * cw * ch
+
+    def walk_lines(f):
+        base = f * per
+        for y in range(h):
+            cl = y // sy
+            Y = work[base + y * w: base + (y + 1) * w]
+            U = work[base + w * h + cl * cw: base + w * h + (cl + 1) * cw]
+            V = work[base + w * h + cw * ch + cl * cw: base + w * h + cw * ch + (cl + 1) * cw]
+            hw.vfgs_add_grain_line(Y, U, V, y, w)
+
+    walk_lines(0)
+    mid = run_device(hw, work[per:2 * per].copy(), 1, w, h, 0, depth)
+    work[per:2 * per] = mid
+    walk_lines(2)
+    assert np.array_equal(work, exp), first_mismatch(work, exp, w, h, fmt, 3)
+    assert hw.get_lfsr() == o.get_lfsr()
+
+
+def test_split_calls_and_skip_frames_equal_one_call(hw):
+    """Frame sharding property: [0,N) in one call == two consecutive calls == skip + second half."""
+    case = "fgs_sei_ff_test6.cfg|d10|420|g100"
+    w, h, n = 640, 360, 6
+    frames = synth_frames(n, w, h, "420", 10, seed=17)
+    per = frames.size // n
+    hw.reset(); program_case(hw, G, case)
+    whole = run_device(hw, frames, n, w, h, 0, 10)
+    regs_whole = hw.get_lfsr()
+    hw.reset(); program_case(hw, G, case)
+    a = run_device(hw, frames[:2 * per].copy(), 2, w, h, 0, 10)
+    b = run_device(hw, frames[2 * per:].copy(), n - 2, w, h, 0, 10)
+    assert np.array_equal(np.concatenate([a, b]), whole)
+    assert hw.get_lfsr() == regs_whole
+    hw.reset(); program_case(hw, G, case)
+    hw.skip_frames(4, w, h)
+    tail = run_device(hw, frames[4 * per:].copy(), n - 4, w, h, 0, 10)
+    assert np.array_equal(tail, whole[4 * per:])
+    assert hw.get_lfsr() == regs_whole
+
+
+def test_padded_strides_and_unaligned_base(hw):
+    """Explicit planes with yuv_alloc-style 64-sample strides (yuv.c:65,74) and a base pointer that
+    defeats the 128-bit path: same samples as the packed layout."""
+    import torch
+    from versatilefilmgrain_b200.api import Planes
+    case = "fgs_sei_ff_test5.cfg|d10|420|g100"
+    w, h, n = 200, 130, 2
+    cw, ch = w // 2, h // 2
+    frames = synth_frames(n, w, h, "420", 10, seed=23)
+    o = Oracle(); program_case(o, G, case)
+    exp = o.add_grain_frames(frames, n, w, h, 0)
+    stride, cstride = 256, 128
+    fsz = stride * h + 2 * cstride * ch
+    for shift in (0, 1):  # shift in samples: 1 -> 2-byte aligned only
+        padded = np.zeros(n * fsz + 8, dtype=np.uint16)
+        per = w * h + 2 * cw * ch
+        for f in range(n):
+            b = shift + f * fsz
+            padded[b: b + stride * h].reshape(h, stride)[:, :w] = frames[f * per: f * per + w * h].reshape(h, w)
+            for c in range(2):
+                src = frames[f * per + w * h + c * cw * ch: f * per + w * h + (c + 1) * cw * ch].reshape(ch, cw)
+                padded[b + stride * h + c * cstride * ch: b + stride * h + (c + 1) * cstride * ch].reshape(ch, cstride)[:, :cw] = src
+        d_in = to_dev(padded)
+        d_out = torch.zeros_like(d_in)
+        base_in, base_out = d_in.data_ptr() + 2 * shift, d_out.data_ptr() + 2 * shift
+        def planes(base):
+            return Planes(base, base + 2 * stride * h, base + 2 * (stride * h + cstride * ch), 2 * stride, 2 * cstride, 2 * fsz)
+        hw.reset(); program_case(hw, G, case)
+        hw.add_grain_planes_device(planes(base_in), planes(base_out), n, w, h, 0, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        res = from_dev(d_out, np.uint16)
+        got = np.zeros_like(frames)
+        for f in range(n):
+            b = shift + f * fsz
+            got[f * per: f * per + w * h] = res[b: b + stride * h].reshape(h, stride)[:, :w].reshape(-1)
+            for c in range(2):
+                blk = res[b + stride * h + c * cstride * ch: b + stride * h + (c + 1) * cstride * ch].reshape(ch, cstride)[:, :cw]
+                got[f * per + w * h + c * cw * ch: f * per + w * h + (c + 1) * cw * ch] = blk.reshape(-1)
+        assert np.array_equal(got, exp), (shift, first_mismatch(got, exp, w, h, "420", n))
+        # nothing outside the picture was written
+        mask = np.ones(res.shape, dtype=bool)
+        for f in range(n):
+            b = shift + f * fsz
+            mask[b: b + stride * h].reshape(h, stride)[:, :w] = False
+            for c in range(2):
+                mask[b + stride * h + c * cstride * ch: b + stride * h + (c + 1) * cstride * ch].reshape(ch, cstride)[:, :cw] = False
+        assert not res[mask].any()
+
+
+FULL_SIZE = [
+    # BASELINE.json configs at their full picture sizes (frame counts kept to what the oracle does in seconds)
+    ("fgs_sei_ff_test1.cfg|d10|420|g100", 1920, 1080, 3, 0),
+    ("fgs_sei_ar_test1.cfg|d10|420|g100", 1920, 1080, 3, 0),
+    ("fgs_afgs1_test1.cfg|d10|420|g100", 3840, 2160, 2, 8),
+    ("fgs_afgs1_test1.cfg|d10|420|g100", 3840, 2160, 2, 0),
+    ("fgs_sei_ff_test4.cfg|d10|422|g150", 3840, 2160, 1, 0),
+    ("fgs_sei_ff_test4.cfg|d10|444|g150", 3840, 2160, 1, 0),
+    ("fgs_sei.cfg|d10|420|g100", 3840, 2160, 1, 0),
+    ("fgs_sei_ff_test1.cfg|d10|420|g100", 7680, 4320, 1, 0),
+]
+
+
+@pytest.mark.parametrize("case,w,h,n,od", FULL_SIZE)
+def test_baseline_configs_full_size(hw, case, w, h, n, od):
+    meta = G.cases[case]
+    frames = synth_frames(n, w, h, meta["fmt"], meta["depth"], seed=w + n)
+    hw.reset(); program_case(hw, G, case)
+    got = run_device(hw, frames, n, w, h, od, meta["depth"])
+    o = Oracle(); program_case(o, G, case)
+    exp = o.add_grain_frames(frames, n, w, h, od)
+    assert np.array_equal(got, exp), first_mismatch(got, exp, w, h, meta["fmt"], n)
+    assert hw.get_lfsr() == o.get_lfsr()
+
+
+def test_large_batch_jump_ahead_matches_continuation(hw):
+    """8K config: frame 2399's grain from a jump of 2399 frames == the last frame of a sequential
+    walk, checked through register state and through one processed frame (checksum of checksums)."""
+    case = "fgs_sei_ff_test1.cfg|d10|420|g100"
+    w, h = 7680, 4320
+    o = Oracle(); program_case(o, G, case)
+    hw.reset(); program_case(hw, G, case)
+    hw.skip_frames(2399, w, h)
+    nb, R = w // 16, h // 16
+    start = int(G.state(case)["lfsr"][2])
+    assert hw.get_lfsr()[2] == o.lfsr_jump(start, 2399 * (R - 1) * nb)
+    frames = synth_frames(1, w, h, "420", 10, seed=1)
+    got = run_device(hw, frames, 1, w, h, 0, 10)
+    o.set_lfsr(hw_regs := [o.lfsr_jump(start, 2399 * (R - 1) * nb + nb), o.lfsr_jump(start, 2399 * (R - 1) * nb),
+                           o.lfsr_jump(start, 2399 * (R - 1) * nb), o.lfsr_jump(start, 2399 * (R - 1) * nb - nb)])
+    exp = o.add_grain_frames(frames, 1, w, h, 0)
+    assert np.array_equal(got, exp)
+
+
+def test_launch_accounting(hw):
+    hw.reset(); program_case(hw, G, "fgs_afgs1_test1.cfg|d10|420|g100")
+    before = hw.launch_count()
+    frames = synth_frames(1, 256, 144, "420", 10, seed=1)
+    run_device(hw, frames, 1, 256, 144, 0, 10)
+    assert hw.launch_count() == before + 2          # LFSR stream kernel + grain kernel
+    ll = hw.last_launch()
+    assert ll["block"] == 256 and ll["grid"] >= 1 and ll["sms"] >= 100

@@ -1,0 +1,108 @@
+"""Shared helpers for the test-suite (fixtures decoding, state programming, digests)."""
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+
+import numpy as np
+
+from oracle.pyoracle import Oracle, program_hw_from_state, synth_frames  # noqa: F401
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden.npz")
+
+
+class Golden:
+    def __init__(self, path=GOLDEN):
+        z = np.load(path)
+        self.arrays = {k: z[k] for k in z.files}
+        meta = json.loads(bytes(self.arrays.pop("__index__")).decode())
+        self.cases, self.kat, self.seed = meta["cases"], meta["kat"], meta["seed"]
+
+    def runnable(self):
+        return [c for c, m in self.cases.items() if m.get("load_rc") == 0 and "outputs" in m]
+
+    def state(self, case: str) -> dict:
+        """Full hw state dict (pattern[2][9][64][64], slut, plut, scalars, lfsr) of a case."""
+        pat = np.zeros((2, 9, 64, 64), dtype=np.int8)
+        luma, chroma = self.arrays[case + "/luma"], self.arrays[case + "/chroma"]
+        pat[0, :luma.shape[0]] = luma
+        pat[1, :chroma.shape[0]] = chroma
+        return {"pattern": pat, "slut": self.arrays[case + "/slut"], "plut": self.arrays[case + "/plut"],
+                "scalars": self.arrays[case + "/scalars"], "lfsr": self.arrays[case + "/lfsr"]}
+
+    def struct(self, case: str) -> bytes:
+        return self.arrays[case + "/struct"].tobytes()
+
+
+def load_golden() -> Golden:
+    return Golden()
+
+
+def sha(a: np.ndarray) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def parse_output_key(key: str):
+    """'256x152x3|s11|o8' -> (w, h, n, input seed, out depth)."""
+    dims, s, o = key.split("|")
+    w, h, n = (int(v) for v in dims.split("x"))
+    return w, h, n, int(s[1:]), int(o[1:])
+
+
+def program_case(hw, golden: Golden, case: str) -> dict:
+    """Reset-free programming of any vfgs_hw.h-shaped object from a golden case; the LFSR registers
+    are set raw so that the default (odd) register value 0xdeadbeef is reproducible too."""
+    st = golden.state(case)
+    program_hw_from_state(hw, st)
+    hw.set_lfsr([int(v) for v in st["lfsr"]])
+    return st
+
+
+def states_equal(a: dict, b: dict, nslot=None) -> list:
+    """Names of the fields that differ. nslot = [luma, chroma] restricts the pattern comparison to
+    the slots the pattern LUTs can select (the fixtures keep only those)."""
+    bad = []
+    for k in ("slut", "plut", "scalars", "lfsr"):
+        if not np.array_equal(np.asarray(a[k]), np.asarray(b[k])):
+            bad.append(k)
+    pa, pb = np.asarray(a["pattern"]), np.asarray(b["pattern"])
+    if nslot is None:
+        if not np.array_equal(pa, pb):
+            bad.append("pattern")
+    else:
+        for bank in range(2):
+            if not np.array_equal(pa[bank, :nslot[bank]], pb[bank, :nslot[bank]]):
+                bad.append(f"pattern[{bank}]")
+    return bad
+
+
+def first_mismatch(a: np.ndarray, b: np.ndarray, width, height, fmt, nframes):
+    """Human-readable location of the first differing sample of two packed planar buffers."""
+    from oracle.pyoracle import frame_samples
+    idx = np.nonzero(a != b)[0]
+    if idx.size == 0:
+        return "identical"
+    i = int(idx[0])
+    ys, cs, cw, _ = frame_samples(width, height, fmt)
+    per = ys + 2 * cs
+    f, r = divmod(i, per)
+    if r < ys:
+        c, y, x = 0, r // width, r % width
+    else:
+        r -= ys
+        c = 1 + r // cs
+        r %= cs
+        y, x = r // cw, r % cw
+    return f"{idx.size} samples differ; first at frame {f} comp {c} line {y} col {x}: got {int(a[i])} want {int(b[i])}"
+
+
+def build_emu() -> str:
+    """Host build of the kernel's per-lane task code (tests/emu/emu.cpp), test tool only."""
+    import subprocess
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu")
+    so, src = os.path.join(here, "libemu.so"), os.path.join(here, "emu.cpp")
+    deps = [src] + [os.path.join(os.path.dirname(here), "..", "versatilefilmgrain_b200", "csrc", n) for n in ("fgs_task.h", "vfgs_core.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", so, src], check=True)
+    return so

@@ -1,0 +1,57 @@
+"""Build recipe for libvfgs_b200.so (in-tree, sm_100a only).
+
+    python -m versatilefilmgrain_b200.build
+
+One nvcc invocation; the resulting shared library sits next to this file (git-ignored, but it
+travels to the GPU box with the repo snapshot).
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libvfgs_b200.so")
+SOURCES = [os.path.join(CSRC, "vfgs_b200.cu")]
+HEADERS = [os.path.join(CSRC, n) for n in ("vfgs_core.h", "fgs_task.h", "vfgs_kernels.cuh")] + [
+    os.path.join(os.path.dirname(HERE), "include", n) for n in ("vfgs_hw.h", "vfgs_b200.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "-Xcompiler", "-fPIC",
+    "--shared", "-cudart", "static",
+]
+
+
+def nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise FileNotFoundError("nvcc not found")
+
+
+def stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(f) > t for f in SOURCES + HEADERS + [os.path.abspath(__file__)])
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not stale():
+        return LIB
+    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    if out.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + out.stdout + out.stderr)
+    if verbose:
+        print(out.stdout + out.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,712 @@
+// vfgs_b200.cu -- C-ABI shim of libvfgs_b200.so: the host mirror of the reference's hardware
+// state (vfgs_hw.c:49-63), its ten setters/entry points (vfgs_hw.c:288-388) and the additive
+// frame-batch entry points of include/vfgs_b200.h. All sample processing happens in the CUDA
+// kernels of vfgs_kernels.cuh; the host only keeps state, builds the table image, does the LFSR
+// register bookkeeping by GF(2) jump-ahead and drives streams.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "../../include/vfgs_b200.h"
+#include "../../include/vfgs_hw.h"
+#include "vfgs_kernels.cuh"
+
+using namespace vfgs;
+
+namespace {
+
+// ------------------------------------------------------------------------------------ state
+constexpr int kSlots = 9; // 8 settable + the always-zero slot 8 (vfgs_hw.c:49)
+
+struct HwState {
+	int8_t pattern[2][kSlots][64][64];
+	uint8_t slut[3][256];
+	uint8_t plut[3][256];
+	uint32_t rnd, rnd_up, line_rnd, line_rnd_up;
+	int scale_shift, bs;
+	int y_min, y_max, c_min, c_max;
+	int csubx, csuby;
+	void power_on()
+	{
+		memset(pattern, 0, sizeof(pattern));
+		memset(slut, 0, sizeof(slut));
+		memset(plut, 0, sizeof(plut));
+		rnd = rnd_up = line_rnd = line_rnd_up = 0xdeadbeefu; // vfgs_hw.c:52-55
+		scale_shift = 5 + 6;                                 // vfgs_hw.c:56
+		bs = 0;
+		y_min = c_min = 0; y_max = c_max = 255;
+		csubx = csuby = 2;
+	}
+};
+
+struct Slot { // one stage of the host pipeline
+	uint8_t* d_in = nullptr;
+	uint8_t* d_out = nullptr;
+	uint32_t* d_streams = nullptr;
+	size_t in_cap = 0, out_cap = 0, streams_cap = 0;
+	cudaEvent_t h2d_done = nullptr, k_done = nullptr, d2h_done = nullptr;
+};
+constexpr int kPipeSlots = 3;
+
+struct Context {
+	bool ready = false;
+	int device = -1;
+	int sm_count = 0;
+	int max_smem_optin = 0;
+	uint32_t* d_pow2 = nullptr;
+	uint8_t* d_blob = nullptr;
+	size_t blob_cap = 0;
+	uint32_t* d_streams = nullptr; // device entry point / line path
+	size_t streams_cap = 0;
+	cudaStream_t last_stream = nullptr;
+	bool used_stream = false;
+	cudaStream_t s_h2d = nullptr, s_k = nullptr, s_d2h = nullptr;
+	Slot slot[kPipeSlots];
+	uint8_t* d_line = nullptr; // compat line path staging
+	size_t line_cap = 0;
+	int smem_attr = 0;
+	int last_launch[4] = {0, 0, 0, 0};
+	// optional per-launch timing of the grain kernel (vfgs_b200_kernel_timing)
+	bool timing = false;
+	std::vector<cudaEvent_t> ev_begin, ev_end;
+	size_t ev_used = 0;
+	double timed_ms = 0.0;
+	uint64_t timed_launches = 0;
+};
+
+HwState g_hw;
+bool g_hw_init = false;
+Context g_ctx;
+bool g_dirty = true; // table image must be rebuilt + uploaded
+std::vector<uint8_t> g_blob;
+struct BlobInfo {
+	int lut_off, pat_off[2], pat_size[2], pat_stride[2], uniform_pi[3], bytes;
+} g_bi;
+uint64_t g_launches = 0;
+char g_err[512] = "";
+const JumpTable& jump_table()
+{
+	static const JumpTable t;
+	return t;
+}
+
+HwState& hw()
+{
+	if (!g_hw_init) { g_hw.power_on(); g_hw_init = true; }
+	return g_hw;
+}
+
+int set_err(int code, const char* fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+	return code;
+}
+
+[[noreturn]] void fatal(const char* what)
+{
+	fprintf(stderr, "vfgs_b200: %s%s%s\n", what, g_err[0] ? ": " : "", g_err);
+	abort();
+}
+
+#define REQUIRE(cond) \
+	do { if (!(cond)) { snprintf(g_err, sizeof(g_err), "%s", #cond); fatal("precondition failed (the reference asserts here)"); } } while (0)
+
+#define CUDA_TRY(expr) \
+	do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return set_err(VFGS_B200_ERR_CUDA, "%s -> %s", #expr, cudaGetErrorString(e_)); } while (0)
+
+// ------------------------------------------------------------------------------------ device ctx
+int ensure_ctx(int device)
+{
+	Context& c = g_ctx;
+	if (c.ready && (device < 0 || device == c.device)) {
+		CUDA_TRY(cudaSetDevice(c.device));
+		return VFGS_B200_OK;
+	}
+	if (c.ready) return set_err(VFGS_B200_ERR_ARG, "library already bound to device %d", c.device);
+	if (device < 0) CUDA_TRY(cudaGetDevice(&device));
+	CUDA_TRY(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+	if (prop.major < 10)
+		return set_err(VFGS_B200_ERR_CUDA, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
+	c.device = device;
+	c.sm_count = prop.multiProcessorCount;
+	c.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+	CUDA_TRY(cudaMalloc(&c.d_pow2, sizeof(uint32_t) * kJumpBits * 32));
+	CUDA_TRY(cudaMemcpy(c.d_pow2, jump_table().pow2, sizeof(uint32_t) * kJumpBits * 32, cudaMemcpyHostToDevice));
+	CUDA_TRY(cudaStreamCreateWithFlags(&c.s_h2d, cudaStreamNonBlocking));
+	CUDA_TRY(cudaStreamCreateWithFlags(&c.s_k, cudaStreamNonBlocking));
+	CUDA_TRY(cudaStreamCreateWithFlags(&c.s_d2h, cudaStreamNonBlocking));
+	for (Slot& s : c.slot) {
+		CUDA_TRY(cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
+		CUDA_TRY(cudaEventCreateWithFlags(&s.k_done, cudaEventDisableTiming));
+		CUDA_TRY(cudaEventCreateWithFlags(&s.d2h_done, cudaEventDisableTiming));
+	}
+	c.ready = true;
+	g_dirty = true;
+	return VFGS_B200_OK;
+}
+
+template <typename T>
+int grow(T*& p, size_t& cap, size_t need)
+{
+	if (need <= cap) return VFGS_B200_OK;
+	if (p) CUDA_TRY(cudaFree(p));
+	p = nullptr; cap = 0;
+	need = (need + 255) & ~(size_t)255;
+	CUDA_TRY(cudaMalloc((void**)&p, need));
+	cap = need;
+	return VFGS_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------ table image
+// Layout (all offsets multiples of 16): LUT uint16[3][256] = scale | slot << 8, then the luma slots in
+// use (4096 B each), then the chroma slots in use packed to (64/csuby) rows x (64/csubx) bytes.
+void build_blob()
+{
+	const HwState& h = hw();
+	int nslot[2] = {1, 1};
+	for (int c = 0; c < 3; c++) {
+		int first = h.plut[c][0] >> 4, uni = first;
+		for (int i = 0; i < 256; i++) {
+			int s = h.plut[c][i] >> 4;
+			if (s != first) uni = -1;
+			if (s + 1 > nslot[c ? 1 : 0]) nslot[c ? 1 : 0] = s + 1;
+		}
+		g_bi.uniform_pi[c] = uni;
+	}
+	const int crows = 64 / h.csuby, ccols = 64 / h.csubx;
+	g_bi.lut_off = 0;
+	g_bi.pat_off[0] = 3 * 256 * 2;
+	g_bi.pat_size[0] = 64 * 64; g_bi.pat_stride[0] = 64;
+	g_bi.pat_off[1] = g_bi.pat_off[0] + nslot[0] * 4096;
+	g_bi.pat_size[1] = crows * ccols; g_bi.pat_stride[1] = ccols;
+	g_bi.bytes = (g_bi.pat_off[1] + nslot[1] * g_bi.pat_size[1] + 16 + 15) & ~15; // +16: fetch8 may touch one word past an octet
+	g_blob.assign((size_t)g_bi.bytes, 0);
+	uint16_t* lut = (uint16_t*)g_blob.data();
+	for (int c = 0; c < 3; c++)
+		for (int i = 0; i < 256; i++) lut[c * 256 + i] = (uint16_t)(h.slut[c][i] | ((h.plut[c][i] >> 4) << 8));
+	for (int s = 0; s < nslot[0]; s++) memcpy(&g_blob[g_bi.pat_off[0] + s * 4096], h.pattern[0][s], 4096);
+	for (int s = 0; s < nslot[1]; s++)
+		for (int r = 0; r < crows; r++)
+			memcpy(&g_blob[g_bi.pat_off[1] + s * g_bi.pat_size[1] + r * ccols], h.pattern[1][s][r], (size_t)ccols);
+}
+
+int upload_blob()
+{
+	if (!g_dirty) return VFGS_B200_OK;
+	Context& c = g_ctx;
+	build_blob();
+	if (g_bi.bytes > c.max_smem_optin - 1024)
+		return set_err(VFGS_B200_ERR_STATE, "table image of %d bytes exceeds shared memory", g_bi.bytes);
+	// frames still in flight read the old image: drain before overwriting (config changes are rare)
+	CUDA_TRY(cudaDeviceSynchronize());
+	if (int rc = grow(c.d_blob, c.blob_cap, (size_t)g_bi.bytes)) return rc;
+	CUDA_TRY(cudaMemcpy(c.d_blob, g_blob.data(), (size_t)g_bi.bytes, cudaMemcpyHostToDevice));
+	if (g_bi.bytes > c.smem_attr) {
+		CUDA_TRY(cudaFuncSetAttribute(fgs_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_bi.bytes));
+		c.smem_attr = g_bi.bytes;
+	}
+	g_dirty = false;
+	return VFGS_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------ launch
+struct Geometry {
+	int width, height, cw, ch, nb, R, wpr;
+	int in_depth, out_depth;
+	size_t in_sample, out_sample;
+	size_t ysam, csam;
+	size_t in_frame_bytes, out_frame_bytes;
+};
+
+int make_geometry(Geometry& g, int width, int height, int out_depth)
+{
+	const HwState& h = hw();
+	// what add_grain_block asserts (vfgs_hw.c:168-170)
+	if (width <= 128) return set_err(VFGS_B200_ERR_STATE, "width must exceed 128 (vfgs_hw.c:168)");
+	if (h.scale_shift + h.bs < 8 || h.scale_shift + h.bs > 13)
+		return set_err(VFGS_B200_ERR_STATE, "scale_shift %d + bs %d outside 8..13 (vfgs_hw.c:170)", h.scale_shift, h.bs);
+	if (height < 1) return set_err(VFGS_B200_ERR_ARG, "height %d", height);
+	g.in_depth = 8 + h.bs;
+	g.out_depth = out_depth ? out_depth : g.in_depth;
+	if (g.out_depth != g.in_depth && !(g.out_depth == 8 && g.in_depth == 10))
+		return set_err(VFGS_B200_ERR_ARG, "out_depth %d with input depth %d", out_depth, g.in_depth);
+	g.width = width; g.height = height;
+	g.cw = width / h.csubx; g.ch = height / h.csuby; // yuv.c:72-77
+	g.nb = (width + 15) / 16; g.R = (height + 15) / 16;
+	g.wpr = ((g.nb + 31) >> 5) + 3;
+	g.in_sample = g.in_depth > 8 ? 2 : 1; g.out_sample = g.out_depth > 8 ? 2 : 1;
+	g.ysam = (size_t)width * height; g.csam = (size_t)g.cw * g.ch;
+	g.in_frame_bytes = (g.ysam + 2 * g.csam) * g.in_sample;
+	g.out_frame_bytes = (g.ysam + 2 * g.csam) * g.out_sample;
+	return VFGS_B200_OK;
+}
+
+bool aligned_for(const void* base, long long row, long long frame, size_t unit)
+{
+	return ((uintptr_t)base % unit) == 0 && (row % (long long)unit) == 0 && (frame % (long long)unit) == 0;
+}
+
+void fill_common(FgsParams& p, const Geometry& g)
+{
+	const HwState& h = hw();
+	memset(&p, 0, sizeof(p));
+	p.nb = g.nb; p.R = g.R;
+	p.subx = h.csubx; p.suby = h.csuby;
+	p.in_bytes = (int)g.in_sample; p.out_bytes = (int)g.out_sample;
+	p.bs = h.bs; p.ss = h.scale_shift;
+	for (int c = 0; c < 3; c++) {
+		p.lo[c] = (c ? h.c_min : h.y_min) << h.bs;
+		p.hi[c] = (c ? h.c_max : h.y_max) << h.bs;
+		p.uniform_pi[c] = g_bi.uniform_pi[c];
+	}
+	p.blob = g_ctx.d_blob; p.blob_bytes = g_bi.bytes;
+	p.lut_off = g_bi.lut_off;
+	for (int b = 0; b < 2; b++) { p.pat_off[b] = g_bi.pat_off[b]; p.pat_size[b] = g_bi.pat_size[b]; p.pat_stride[b] = g_bi.pat_stride[b]; }
+	p.wpr = g.wpr;
+}
+
+void finish_tasks(FgsParams& p)
+{
+	for (int c = 0; c < 3; c++) {
+		p.nseg[c] = (p.comp[c].width + kSegSamples - 1) / kSegSamples;
+		p.comp[c].vec = aligned_for(p.comp[c].in, p.comp[c].in_row_bytes, p.in_frame_bytes, 8 * (size_t)p.in_bytes) &&
+		                aligned_for(p.comp[c].out, p.comp[c].out_row_bytes, p.out_frame_bytes, 8 * (size_t)p.out_bytes);
+	}
+	p.tasks_per_stripe = p.nseg[0] + p.nseg[1] + p.nseg[2];
+	p.total_tasks = (long long)p.nframes * p.rows * p.tasks_per_stripe;
+}
+
+int launch_apply(const FgsParams& p, cudaStream_t stream)
+{
+	Context& c = g_ctx;
+	if (p.total_tasks <= 0) return VFGS_B200_OK;
+	int per_sm = 0;
+	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fgs_apply_kernel, kCtaThreads, (size_t)p.blob_bytes));
+	if (per_sm < 1) return set_err(VFGS_B200_ERR_CUDA, "grain kernel does not fit on an SM (smem %d)", p.blob_bytes);
+	long long want = (p.total_tasks + kWarpsPerCta - 1) / kWarpsPerCta;
+	long long cap = (long long)c.sm_count * per_sm; // persistent grid: a whole number of CTAs per SM
+	int grid = (int)(want < cap ? want : cap);
+	cudaEvent_t e0 = nullptr, e1 = nullptr;
+	if (c.timing) {
+		if (c.ev_used == c.ev_begin.size()) {
+			cudaEvent_t a, b;
+			CUDA_TRY(cudaEventCreate(&a));
+			CUDA_TRY(cudaEventCreate(&b));
+			c.ev_begin.push_back(a); c.ev_end.push_back(b);
+		}
+		e0 = c.ev_begin[c.ev_used]; e1 = c.ev_end[c.ev_used]; c.ev_used++;
+		CUDA_TRY(cudaEventRecord(e0, stream));
+	}
+	fgs_apply_kernel<<<grid, kCtaThreads, (size_t)p.blob_bytes, stream>>>(p);
+	CUDA_TRY(cudaGetLastError());
+	if (c.timing) CUDA_TRY(cudaEventRecord(e1, stream));
+	g_launches++;
+	c.last_launch[0] = grid; c.last_launch[1] = kCtaThreads; c.last_launch[2] = p.blob_bytes; c.last_launch[3] = c.sm_count;
+	return VFGS_B200_OK;
+}
+
+int launch_streams(uint32_t epoch, uint32_t* d_streams, int nframes, const Geometry& g, uint64_t frame0, cudaStream_t stream)
+{
+	const long long warps = (long long)nframes * g.R;
+	const int grid = (int)((warps * 32 + kCtaThreads - 1) / kCtaThreads);
+	lfsr_streams_kernel<<<grid, kCtaThreads, 0, stream>>>(epoch, g_ctx.d_pow2, d_streams, nframes, g.R, g.nb, g.wpr, frame0);
+	CUDA_TRY(cudaGetLastError());
+	g_launches++;
+	return VFGS_B200_OK;
+}
+
+// Register state after nframes whole frames (vfgs_hw.c:291-298,309-310 in closed form).
+void advance_registers(const Geometry& g, uint64_t nframes)
+{
+	if (!nframes) return;
+	HwState& h = hw();
+	const JumpTable& jt = jump_table();
+	const uint32_t s0 = h.line_rnd;
+	const uint64_t adv = nframes * (uint64_t)(g.R - 1) * (uint64_t)g.nb;
+	if (g.R >= 2) {
+		h.line_rnd_up = jt.jump(s0, adv - (uint64_t)g.nb);
+		h.line_rnd = jt.jump(s0, adv);
+	}
+	h.rnd = jt.jump(h.line_rnd, (uint64_t)g.nb);
+	h.rnd_up = jt.jump(h.line_rnd_up, (uint64_t)g.nb);
+}
+
+// Streams + grain kernels for `n` frames whose epoch-relative index starts at frame0.
+int run_frames_device(const vfgs_b200_planes& in, const vfgs_b200_planes& out, int n, const Geometry& g,
+                      uint32_t epoch, uint64_t frame0, uint32_t* d_streams, cudaStream_t stream)
+{
+	FgsParams p;
+	fill_common(p, g);
+	p.nframes = n;
+	p.y_begin = 0; p.y_end = g.height;
+	p.row_begin = 0; p.rows = g.R;
+	p.in_frame_bytes = in.frame_stride; p.out_frame_bytes = out.frame_stride;
+	const void* ip[3] = {in.y, in.u, in.v};
+	void* op[3] = {out.y, out.u, out.v};
+	for (int c = 0; c < 3; c++) {
+		p.comp[c].in = (const uint8_t*)ip[c]; p.comp[c].out = (uint8_t*)op[c];
+		p.comp[c].in_row_bytes = c ? in.stride_c : in.stride_y;
+		p.comp[c].out_row_bytes = c ? out.stride_c : out.stride_y;
+		p.comp[c].width = c ? g.cw : g.width;
+		p.comp[c].lines = c ? g.ch : g.height;
+	}
+	p.streams = d_streams; p.stream_rows = g.R; p.stream_row0 = 0;
+	finish_tasks(p);
+	if (int rc = launch_streams(epoch, d_streams, n, g, frame0, stream)) return rc;
+	return launch_apply(p, stream);
+}
+
+void packed_planes(vfgs_b200_planes& pl, const void* base, const Geometry& g, size_t sample, size_t frame_bytes)
+{
+	uint8_t* b = (uint8_t*)base;
+	pl.y = b; pl.u = b + g.ysam * sample; pl.v = b + (g.ysam + g.csam) * sample;
+	pl.stride_y = (int64_t)(g.width * sample); pl.stride_c = (int64_t)(g.cw * sample);
+	pl.frame_stride = (int64_t)frame_bytes;
+}
+
+bool all_uniform() { return g_bi.uniform_pi[0] >= 0 && g_bi.uniform_pi[1] >= 0 && g_bi.uniform_pi[2] >= 0; }
+
+int prepare(int device)
+{
+	if (int rc = ensure_ctx(device)) return rc;
+	return upload_blob();
+}
+
+} // namespace
+
+// ====================================================================================== vfgs_hw.h
+extern "C" {
+
+void vfgs_set_luma_pattern(int index, int8_t* P) // vfgs_hw.c:314-318
+{
+	REQUIRE(index >= 0 && index < VFGS_MAX_PATTERNS);
+	memcpy(hw().pattern[0][index], P, 64 * 64);
+	g_dirty = true;
+}
+
+void vfgs_set_chroma_pattern(int index, int8_t* P) // vfgs_hw.c:320-325
+{
+	REQUIRE(index >= 0 && index < VFGS_MAX_PATTERNS);
+	HwState& h = hw();
+	const int rows = 64 / h.csuby, src_stride = 64 / h.csuby, ncopy = 64 / h.csubx;
+	for (int r = 0; r < rows; r++) memcpy(h.pattern[1][index][r], P + (size_t)src_stride * r, (size_t)ncopy);
+	g_dirty = true;
+}
+
+void vfgs_set_scale_lut(int c, uint8_t lut[]) // vfgs_hw.c:327-331
+{
+	REQUIRE(c >= 0 && c < 3);
+	memcpy(hw().slut[c], lut, 256);
+	g_dirty = true;
+}
+
+void vfgs_set_pattern_lut(int c, uint8_t lut[]) // vfgs_hw.c:333-337
+{
+	REQUIRE(c >= 0 && c < 3);
+	// lut[i] >> 4 indexes pattern[..][9] in vfgs_hw.c:218; anything above slot 8 is out of bounds there
+	for (int i = 0; i < 256; i++) REQUIRE((lut[i] >> 4) < kSlots);
+	memcpy(hw().plut[c], lut, 256);
+	g_dirty = true;
+}
+
+void vfgs_set_seed(uint32_t seed) // vfgs_hw.c:339-344
+{
+	HwState& h = hw();
+	h.rnd = h.rnd_up = h.line_rnd = h.line_rnd_up = seed << 1;
+}
+
+void vfgs_set_scale_shift(int shift) // vfgs_hw.c:346-350
+{
+	REQUIRE(shift >= 2 && shift < 8);
+	HwState& h = hw();
+	h.scale_shift = shift + 6 - h.bs;
+}
+
+void vfgs_set_depth(int depth) // vfgs_hw.c:352-362
+{
+	REQUIRE(depth == 8 || depth == 10);
+	HwState& h = hw();
+	const int nbs = depth - 8;
+	h.scale_shift = (h.scale_shift + h.bs - nbs) & 0xff;
+	if (h.bs != nbs) g_dirty = true;
+	h.bs = nbs;
+}
+
+void vfgs_set_legal_range(int legal) // vfgs_hw.c:364-380
+{
+	HwState& h = hw();
+	h.y_min = h.c_min = legal ? 16 : 0;
+	h.y_max = legal ? 235 : 255;
+	h.c_max = legal ? 240 : 255;
+}
+
+void vfgs_set_chroma_subsampling(int subx, int suby) // vfgs_hw.c:382-388
+{
+	REQUIRE(subx == 1 || subx == 2);
+	REQUIRE(suby == 1 || suby == 2);
+	HwState& h = hw();
+	if (h.csubx != subx || h.csuby != suby) g_dirty = true;
+	h.csubx = subx; h.csuby = suby;
+}
+
+// vfgs_hw.c:288-312. Host line buffers, in place, synchronous. The register bookkeeping is the
+// reference's; the samples go through the same kernels as the frame entry points.
+void vfgs_add_grain_line(void* Y, void* U, void* V, int y, int width)
+{
+	HwState& h = hw();
+	Geometry g;
+	if (make_geometry(g, width, 16 * ((y >> 4) + 1), 0)) fatal("vfgs_add_grain_line");
+	if (prepare(-1)) fatal("vfgs_add_grain_line");
+	Context& c = g_ctx;
+	const JumpTable& jt = jump_table();
+
+	if (y && (y & 15) == 0) { h.line_rnd_up = h.line_rnd; h.line_rnd = h.rnd; }
+
+	// two stream rows (upper, current) generated on the host: nb + a few words, trivial
+	std::vector<uint32_t> rows((size_t)2 * g.wpr);
+	uint32_t su = h.line_rnd_up, sc = h.line_rnd;
+	for (int w = 0; w < g.wpr; w++) {
+		rows[w] = su; rows[(size_t)g.wpr + w] = sc;
+		su = jt.jump(su, 32); sc = jt.jump(sc, 32);
+	}
+	const bool chroma = !((y & 1) && h.csuby > 1); // vfgs_hw.c:164-165
+	const size_t lbytes = (size_t)width * g.in_sample, cbytes = (size_t)g.cw * g.in_sample;
+	const size_t lpad = (lbytes + 255) & ~(size_t)255, cpad = (cbytes + 255) & ~(size_t)255;
+	auto chk = [](cudaError_t e, const char* what) {
+		if (e != cudaSuccess) { snprintf(g_err, sizeof(g_err), "%s -> %s", what, cudaGetErrorString(e)); fatal("vfgs_add_grain_line"); }
+	};
+	if (grow(c.d_line, c.line_cap, lpad + 2 * cpad)) fatal("vfgs_add_grain_line");
+	if (grow(c.d_streams, c.streams_cap, rows.size() * sizeof(uint32_t))) fatal("vfgs_add_grain_line");
+	cudaStream_t st = c.s_k;
+	if (c.used_stream && c.last_stream != st) chk(cudaStreamSynchronize(c.last_stream), "sync");
+	c.last_stream = st; c.used_stream = true;
+	chk(cudaMemcpyAsync(c.d_streams, rows.data(), rows.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st), "streams H2D");
+	chk(cudaMemcpyAsync(c.d_line, Y, lbytes, cudaMemcpyHostToDevice, st), "Y H2D");
+	if (chroma) {
+		chk(cudaMemcpyAsync(c.d_line + lpad, U, cbytes, cudaMemcpyHostToDevice, st), "U H2D");
+		chk(cudaMemcpyAsync(c.d_line + lpad + cpad, V, cbytes, cudaMemcpyHostToDevice, st), "V H2D");
+	}
+	FgsParams p;
+	fill_common(p, g);
+	p.nframes = 1;
+	p.y_begin = y; p.y_end = y + 1;
+	p.row_begin = y >> 4; p.rows = 1;
+	uint8_t* base[3] = {c.d_line, c.d_line + lpad, c.d_line + lpad + cpad};
+	for (int k = 0; k < 3; k++) {
+		p.comp[k].in = base[k]; p.comp[k].out = base[k];
+		p.comp[k].in_row_bytes = p.comp[k].out_row_bytes = 0; // every line index maps to the staged line
+		p.comp[k].width = k ? g.cw : width;
+		p.comp[k].lines = (k && !chroma) ? 0 : 0x7fffffff;
+	}
+	p.streams = c.d_streams; p.stream_rows = 2; p.stream_row0 = (y >> 4) - 1;
+	finish_tasks(p);
+	if (launch_apply(p, st)) fatal("vfgs_add_grain_line");
+	chk(cudaMemcpyAsync(Y, c.d_line, lbytes, cudaMemcpyDeviceToHost, st), "Y D2H");
+	if (chroma) {
+		chk(cudaMemcpyAsync(U, c.d_line + lpad, cbytes, cudaMemcpyDeviceToHost, st), "U D2H");
+		chk(cudaMemcpyAsync(V, c.d_line + lpad + cpad, cbytes, cudaMemcpyDeviceToHost, st), "V D2H");
+	}
+	chk(cudaStreamSynchronize(st), "line sync");
+
+	h.rnd = jt.jump(h.line_rnd, (uint64_t)g.nb);
+	h.rnd_up = jt.jump(h.line_rnd_up, (uint64_t)g.nb);
+}
+
+// ====================================================================================== vfgs_b200.h
+int vfgs_b200_init(int device) { return ensure_ctx(device); }
+
+int vfgs_b200_reset(void)
+{
+	g_hw.power_on();
+	g_hw_init = true;
+	g_dirty = true;
+	return VFGS_B200_OK;
+}
+
+const char* vfgs_b200_last_error(void) { return g_err; }
+
+size_t vfgs_b200_frame_bytes(int width, int height, int depth)
+{
+	const HwState& h = hw();
+	const size_t s = depth > 8 ? 2 : 1;
+	return ((size_t)width * height + 2 * (size_t)(width / h.csubx) * (height / h.csuby)) * s;
+}
+
+int vfgs_b200_add_grain_planes_device(const vfgs_b200_planes* in, const vfgs_b200_planes* out, int nframes,
+                                      int width, int height, int out_depth, void* stream)
+{
+	if (!in || !out || nframes < 0) return set_err(VFGS_B200_ERR_ARG, "null planes or negative frame count");
+	Geometry g;
+	if (int rc = make_geometry(g, width, height, out_depth)) return rc;
+	if (int rc = prepare(-1)) return rc;
+	if (nframes == 0) return VFGS_B200_OK;
+	if (in->y == out->y && (g.in_depth != g.out_depth || !all_uniform()))
+		return set_err(VFGS_B200_ERR_ARG, "in-place needs equal depths and one pattern per component");
+	Context& c = g_ctx;
+	cudaStream_t st = (cudaStream_t)stream;
+	if (c.used_stream && c.last_stream != st) CUDA_TRY(cudaStreamSynchronize(c.last_stream)); // d_streams is shared
+	c.last_stream = st; c.used_stream = true;
+	if (int rc = grow(c.d_streams, c.streams_cap, (size_t)nframes * g.R * g.wpr * sizeof(uint32_t))) return rc;
+	if (int rc = run_frames_device(*in, *out, nframes, g, hw().line_rnd, 0, c.d_streams, st)) return rc;
+	advance_registers(g, (uint64_t)nframes);
+	return VFGS_B200_OK;
+}
+
+int vfgs_b200_add_grain_frames_device(const void* in, void* out, int nframes, int width, int height,
+                                      int out_depth, void* stream)
+{
+	if (!in || !out) return set_err(VFGS_B200_ERR_ARG, "null buffer");
+	Geometry g;
+	if (int rc = make_geometry(g, width, height, out_depth)) return rc;
+	vfgs_b200_planes pi, po;
+	packed_planes(pi, in, g, g.in_sample, g.in_frame_bytes);
+	packed_planes(po, out, g, g.out_sample, g.out_frame_bytes);
+	return vfgs_b200_add_grain_planes_device(&pi, &po, nframes, width, height, out_depth, stream);
+}
+
+int vfgs_b200_add_grain_frames_host(const void* in, void* out, int nframes, int width, int height, int out_depth)
+{
+	if (!in || !out || nframes < 0) return set_err(VFGS_B200_ERR_ARG, "null buffer or negative frame count");
+	Geometry g;
+	if (int rc = make_geometry(g, width, height, out_depth)) return rc;
+	if (int rc = prepare(-1)) return rc;
+	if (nframes == 0) return VFGS_B200_OK;
+	if (in == out && g.in_depth != g.out_depth) return set_err(VFGS_B200_ERR_ARG, "in-place needs equal depths");
+	Context& c = g_ctx;
+	if (c.used_stream) { CUDA_TRY(cudaStreamSynchronize(c.last_stream)); c.used_stream = false; }
+
+	// chunk = as many frames as fit ~64 MB of input; the ring has kPipeSlots chunks in flight
+	int per = (int)((64u << 20) / g.in_frame_bytes);
+	if (per < 1) per = 1;
+	if (per > nframes) per = nframes;
+	const uint32_t epoch = hw().line_rnd;
+	const uint8_t* hin = (const uint8_t*)in;
+	uint8_t* hout = (uint8_t*)out;
+	int idx = 0;
+	for (int f0 = 0; f0 < nframes; f0 += per, idx++) {
+		const int n = (nframes - f0 < per) ? nframes - f0 : per;
+		Slot& s = c.slot[idx % kPipeSlots];
+		if (int rc = grow(s.d_in, s.in_cap, (size_t)per * g.in_frame_bytes)) return rc;
+		if (int rc = grow(s.d_out, s.out_cap, (size_t)per * g.out_frame_bytes)) return rc;
+		if (int rc = grow(s.d_streams, s.streams_cap, (size_t)per * g.R * g.wpr * sizeof(uint32_t))) return rc;
+		// the slot's previous chunk must have left the device before its buffers are overwritten
+		if (idx >= kPipeSlots) {
+			CUDA_TRY(cudaStreamWaitEvent(c.s_h2d, s.k_done, 0));   // d_in free once its kernel is done
+			CUDA_TRY(cudaStreamWaitEvent(c.s_k, s.d2h_done, 0));   // d_out free once copied back
+		}
+		CUDA_TRY(cudaMemcpyAsync(s.d_in, hin + (size_t)f0 * g.in_frame_bytes, (size_t)n * g.in_frame_bytes, cudaMemcpyHostToDevice, c.s_h2d));
+		CUDA_TRY(cudaEventRecord(s.h2d_done, c.s_h2d));
+		CUDA_TRY(cudaStreamWaitEvent(c.s_k, s.h2d_done, 0));
+		vfgs_b200_planes pi, po;
+		packed_planes(pi, s.d_in, g, g.in_sample, g.in_frame_bytes);
+		packed_planes(po, s.d_out, g, g.out_sample, g.out_frame_bytes);
+		if (int rc = run_frames_device(pi, po, n, g, epoch, (uint64_t)f0, s.d_streams, c.s_k)) return rc;
+		CUDA_TRY(cudaEventRecord(s.k_done, c.s_k));
+		CUDA_TRY(cudaStreamWaitEvent(c.s_d2h, s.k_done, 0));
+		CUDA_TRY(cudaMemcpyAsync(hout + (size_t)f0 * g.out_frame_bytes, s.d_out, (size_t)n * g.out_frame_bytes, cudaMemcpyDeviceToHost, c.s_d2h));
+		CUDA_TRY(cudaEventRecord(s.d2h_done, c.s_d2h));
+	}
+	CUDA_TRY(cudaStreamSynchronize(c.s_d2h));
+	CUDA_TRY(cudaStreamSynchronize(c.s_k));
+	CUDA_TRY(cudaStreamSynchronize(c.s_h2d));
+	advance_registers(g, (uint64_t)nframes);
+	return VFGS_B200_OK;
+}
+
+int vfgs_b200_skip_frames(int64_t nframes, int width, int height)
+{
+	if (nframes < 0) return set_err(VFGS_B200_ERR_ARG, "negative frame count");
+	Geometry g;
+	if (int rc = make_geometry(g, width, height, 0)) return rc;
+	advance_registers(g, (uint64_t)nframes);
+	return VFGS_B200_OK;
+}
+
+void vfgs_b200_get_lfsr(uint32_t regs[4])
+{
+	const HwState& h = hw();
+	regs[0] = h.rnd; regs[1] = h.rnd_up; regs[2] = h.line_rnd; regs[3] = h.line_rnd_up;
+}
+
+void vfgs_b200_set_lfsr(const uint32_t regs[4])
+{
+	HwState& h = hw();
+	h.rnd = regs[0]; h.rnd_up = regs[1]; h.line_rnd = regs[2]; h.line_rnd_up = regs[3];
+}
+
+// Mirror of the hardware state in the layout of the reference's statics (see oracle/ref_harness.c
+// refh_state): pattern[2][9][64][64], sLUT[3][256], pLUT[3][256], 4 LFSR registers, then
+// scale_shift, bs, Y_min, Y_max, C_min, C_max, csubx, csuby as ints.
+size_t vfgs_b200_get_state(void* dst, size_t cap)
+{
+	const HwState& h = hw();
+	const size_t need = sizeof(h.pattern) + sizeof(h.slut) + sizeof(h.plut) + 4 * sizeof(uint32_t) + 8 * sizeof(int);
+	if (!dst || cap < need) return need;
+	uint8_t* p = (uint8_t*)dst;
+	memcpy(p, h.pattern, sizeof(h.pattern)); p += sizeof(h.pattern);
+	memcpy(p, h.slut, sizeof(h.slut)); p += sizeof(h.slut);
+	memcpy(p, h.plut, sizeof(h.plut)); p += sizeof(h.plut);
+	const uint32_t regs[4] = {h.rnd, h.rnd_up, h.line_rnd, h.line_rnd_up};
+	memcpy(p, regs, sizeof(regs)); p += sizeof(regs);
+	const int sc[8] = {h.scale_shift, h.bs, h.y_min, h.y_max, h.c_min, h.c_max, h.csubx, h.csuby};
+	memcpy(p, sc, sizeof(sc));
+	return need;
+}
+
+void* vfgs_b200_host_alloc(size_t bytes)
+{
+	if (ensure_ctx(-1)) return nullptr;
+	void* p = nullptr;
+	if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+		set_err(VFGS_B200_ERR_CUDA, "cudaHostAlloc(%zu) failed", bytes);
+		return nullptr;
+	}
+	return p;
+}
+
+void vfgs_b200_host_free(void* p)
+{
+	if (p) cudaFreeHost(p);
+}
+
+uint64_t vfgs_b200_launch_count(void) { return g_launches; }
+
+int vfgs_b200_kernel_timing(int enable)
+{
+	if (int rc = ensure_ctx(-1)) return rc;
+	Context& c = g_ctx;
+	c.timing = enable != 0;
+	c.ev_used = 0; c.timed_ms = 0.0; c.timed_launches = 0;
+	return VFGS_B200_OK;
+}
+
+int vfgs_b200_kernel_time(double* total_ms, uint64_t* launches)
+{
+	Context& c = g_ctx;
+	if (!c.ready) return set_err(VFGS_B200_ERR_ARG, "no device bound");
+	for (size_t i = 0; i < c.ev_used; i++) {
+		CUDA_TRY(cudaEventSynchronize(c.ev_end[i]));
+		float ms = 0.f;
+		CUDA_TRY(cudaEventElapsedTime(&ms, c.ev_begin[i], c.ev_end[i]));
+		c.timed_ms += ms; c.timed_launches++;
+	}
+	c.ev_used = 0;
+	if (total_ms) *total_ms = c.timed_ms;
+	if (launches) *launches = c.timed_launches;
+	return VFGS_B200_OK;
+}
+
+void vfgs_b200_last_launch(int out[4])
+{
+	for (int i = 0; i < 4; i++) out[i] = g_ctx.last_launch[i];
+}
+
+} // extern "C"

@@ -1,0 +1,100 @@
+// vfgs_kernels.cuh -- the two CUDA kernels of the hot path (sm_100a).
+//
+//   lfsr_streams_kernel  replaces the serial LFSR chain of vfgs_hw.c:74-79,291-298,309-310: one warp
+//                        per (frame, block-row) jumps the epoch state ahead by
+//                        t = (f (R-1) + r) nb steps with 32x32 GF(2) matrix powers (one output bit
+//                        per lane, gathered by a ballot) and emits the row's bit-stream, 32 bits per
+//                        ballot, from which every block takes its 32-bit window.
+//   fgs_apply_kernel     replaces add_grain_block + vfgs_add_grain_line + the frame walk of
+//                        vfgs_main.c:664-682 + yuv_to_8bit: persistent CTAs copy the LUT/pattern image
+//                        to shared memory with one bulk async copy (TMA engine, cp.async.bulk +
+//                        mbarrier) and then loop over warp-tasks (fgs_task.h) with 128-bit global
+//                        loads and stores.
+#pragma once
+#include <cuda_runtime.h>
+#include "fgs_task.h"
+
+namespace vfgs {
+
+constexpr int kCtaThreads = 256;
+constexpr int kWarpsPerCta = kCtaThreads / 32;
+
+// ---- mbarrier / bulk-copy PTX -------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+	return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+	asm volatile(
+	    "{\n"
+	    ".reg .pred p;\n"
+	    "WAIT_%=:\n"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+	    "@p bra DONE_%=;\n"
+	    "bra WAIT_%=;\n"
+	    "DONE_%=:\n"
+	    "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ---- LFSR bit-streams ----------------------------------------------------------------------
+// streams[(f * R + r) * wpr + w] = register value 32 w steps after block 0 of block-row r of frame
+// frame0 + f, i.e. bits [32w, 32w+32) of that row's stream. pow2 = JumpTable as uint32[64][32].
+__global__ void __launch_bounds__(kCtaThreads)
+lfsr_streams_kernel(uint32_t epoch_state, const uint32_t* __restrict__ pow2, uint32_t* __restrict__ streams,
+                    int nframes, int R, int nb, int wpr, unsigned long long frame0)
+{
+	const int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+	const int lane = threadIdx.x & 31;
+	if (warp >= nframes * R) return; // warp-uniform
+	const int f = warp / R, r = warp - f * R;
+	unsigned long long t = ((frame0 + (unsigned long long)f) * (unsigned long long)(R - 1) + (unsigned long long)r) *
+	                       (unsigned long long)nb;
+	uint32_t s = epoch_state;
+	for (int k = 0; t; k++, t >>= 1)
+		if (t & 1ull) s = __ballot_sync(0xffffffffu, __popc(pow2[k * 32 + lane] & s) & 1);
+	const uint32_t step32 = pow2[5 * 32 + lane];
+	uint32_t* dst = streams + (size_t)warp * wpr;
+	for (int w = 0; w < wpr; w++) {
+		if (lane == 0) dst[w] = s;
+		s = __ballot_sync(0xffffffffu, __popc(step32 & s) & 1);
+	}
+}
+
+// ---- grain synthesis -----------------------------------------------------------------------
+__global__ void __launch_bounds__(kCtaThreads, 4)
+fgs_apply_kernel(const __grid_constant__ FgsParams p)
+{
+	extern __shared__ __align__(128) uint8_t tab[];
+	__shared__ __align__(8) uint64_t bar;
+
+	if (threadIdx.x == 0) mbar_init(&bar, 1);
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		mbar_arrive_expect_tx(&bar, (uint32_t)p.blob_bytes);
+		bulk_copy_g2s(tab, p.blob, (uint32_t)p.blob_bytes, &bar);
+	}
+	mbar_wait(&bar, 0);
+
+	const int lane = threadIdx.x & 31;
+	const long long stride = (long long)gridDim.x * kWarpsPerCta;
+	for (long long task = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); task < p.total_tasks; task += stride)
+		process_task(p, tab, task, lane);
+}
+
+} // namespace vfgs

@@ -98,6 +98,10 @@ uint64_t vfgs_b200_launch_count(void);
 int vfgs_b200_kernel_timing(int enable);
 int vfgs_b200_kernel_time(double* total_ms, uint64_t* launches);
 
+/* Test aid: route every component through the general (sample-adaptive) grain kernel even where
+ * the single-pattern fast kernel would qualify. Both are CUDA paths. */
+void vfgs_b200_force_general_kernel(int on);
+
 /* Geometry of the last grain kernel launch: out[0]=grid, out[1]=block, out[2]=dynamic smem bytes,
  * out[3]=SM count of the bound device. */
 void vfgs_b200_last_launch(int out[4]);

@@ -54,15 +54,20 @@ def test_every_golden_case(hw, case):
     meta = G.cases[case]
     for key, want in meta["outputs"].items():
         w, h, n, iseed, od = parse_output_key(key)
-        hw.reset()
-        program_case(hw, G, case)
         frames = synth_frames(n, w, h, meta["fmt"], meta["depth"], seed=iseed)
-        got = run_device(hw, frames, n, w, h, od, meta["depth"])
         o = Oracle(); program_case(o, G, case)
         exp = o.add_grain_frames(frames, n, w, h, od)
-        assert np.array_equal(got, exp), (case, key, first_mismatch(got, exp, w, h, meta["fmt"], n))
-        assert sha(got) == want["sha256"], (case, key)
-        assert hw.get_lfsr() == want["lfsr_after"], (case, key)
+        for general_only in (False, True):  # fast kernel where it qualifies / general kernel everywhere
+            hw.reset()
+            program_case(hw, G, case)
+            hw.force_general_kernel(general_only)
+            try:
+                got = run_device(hw, frames, n, w, h, od, meta["depth"])
+            finally:
+                hw.force_general_kernel(False)
+            assert np.array_equal(got, exp), (case, key, general_only, first_mismatch(got, exp, w, h, meta["fmt"], n))
+            assert sha(got) == want["sha256"], (case, key)
+            assert hw.get_lfsr() == want["lfsr_after"], (case, key)
 
 
 @pytest.mark.parametrize("case", ["fgs_afgs1_test1.cfg|d10|420|g100", "fgs_sei_ff_test1.cfg|d8|420|g100",
@@ -260,6 +265,26 @@ def test_large_batch_jump_ahead_matches_continuation(hw):
                            o.lfsr_jump(start, 2399 * (R - 1) * nb), o.lfsr_jump(start, 2399 * (R - 1) * nb - nb)])
     exp = o.add_grain_frames(frames, 1, w, h, 0)
     assert np.array_equal(got, exp)
+
+
+def test_out_of_range_codes_and_minus_128_pattern(hw):
+    """16-bit containers with codes above 1023 clip like the reference's int arithmetic (fast kernel's
+    packed 16-bit add must not wrap); a -128 pattern byte cannot be sign-folded and takes the general kernel."""
+    case = "fgs_afgs1_test1.cfg|d10|420|g100"
+    w, h, n = 1024, 80, 2
+    rng = np.random.default_rng(5)
+    frames = rng.integers(0, 65536, size=n * w * h * 3 // 2, dtype=np.uint16)
+    for od in (0, 8):
+        hw.reset(); program_case(hw, G, case)
+        got = run_device(hw, frames, n, w, h, od, 10)
+        o = Oracle(); program_case(o, G, case)
+        assert np.array_equal(got, o.add_grain_frames(frames, n, w, h, od))
+    P = G.state(case)["pattern"][0, 0].copy(); P[5, 7] = -128; P[40, 33] = -128
+    hw.reset(); program_case(hw, G, case); hw.vfgs_set_luma_pattern(0, np.ascontiguousarray(P))
+    o = Oracle(); program_case(o, G, case); o.vfgs_set_luma_pattern(0, np.ascontiguousarray(P))
+    frames = synth_frames(n, w, h, "420", 10, seed=2)
+    got = run_device(hw, frames, n, w, h, 0, 10)
+    assert np.array_equal(got, o.add_grain_frames(frames, n, w, h, 0))
 
 
 def test_launch_accounting(hw):

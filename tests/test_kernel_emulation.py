@@ -16,18 +16,19 @@ CASES = G.runnable()
 @pytest.fixture(scope="module")
 def emu():
     L = C.CDLL(build_emu())
-    L.emu_add_grain_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 5
+    L.emu_add_grain_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 6
     assert L.emu_state_size() == C.sizeof(RefState)
     return L
 
 
-def run_emu(emu, o: Oracle, frames, n, w, h, od, first=0):
+def run_emu(emu, o: Oracle, frames, n, w, h, od, first=0, force_general=False):
+    """Returns (output, mask): mask bit 0 = fast task code ran, bit 1 = general task code ran."""
     st = RefState()
     o.L.oracle_get_state(o.h, C.byref(st))
     depth = 8 + st.bs
     out = np.zeros(frames.shape, dtype=np.uint8 if (od == 8 or depth == 8) else np.uint16)
-    assert emu.emu_add_grain_frames(C.byref(st), _ptr(frames), _ptr(out), n, w, h, od, first) == 0
-    return out
+    mask = emu.emu_add_grain_frames(C.byref(st), _ptr(frames), _ptr(out), n, w, h, od, first, 1 if force_general else 0)
+    return out, mask
 
 
 @pytest.mark.parametrize("case", CASES)
@@ -37,9 +38,11 @@ def test_emulated_kernel_equals_oracle(emu, case):
         for od in ((0, 8) if meta["depth"] == 10 else (0,)):
             o = Oracle(); program_case(o, G, case)
             frames = synth_frames(n, w, h, meta["fmt"], meta["depth"], seed=w + od)
-            got = run_emu(emu, o, frames, n, w, h, od)
-            want = o.add_grain_frames(frames, n, w, h, od)
-            assert np.array_equal(got, want), (case, w, h, od, first_mismatch(got, want, w, h, meta["fmt"], n))
+            runs = [(fg, run_emu(emu, o, frames, n, w, h, od, force_general=fg)) for fg in (False, True)]
+            want = o.add_grain_frames(frames, n, w, h, od)  # advances o's registers: emulate first
+            for force_general, (got, mask) in runs:
+                assert np.array_equal(got, want), (case, w, h, od, force_general, first_mismatch(got, want, w, h, meta["fmt"], n))
+                assert not force_general or mask == 2
 
 
 def test_emulated_kernel_frame_offset(emu):
@@ -51,5 +54,39 @@ def test_emulated_kernel_frame_offset(emu):
     want = o.add_grain_frames(frames, 4, w, h, 0)
     o2 = Oracle(); program_case(o2, G, case)
     per = frames.size // 4
-    got = run_emu(emu, o2, frames[2 * per:].copy(), 2, w, h, 0, first=2)
+    got, _ = run_emu(emu, o2, frames[2 * per:].copy(), 2, w, h, 0, first=2)
     assert np.array_equal(got, want[2 * per:])
+
+
+def test_fast_path_is_taken_where_expected(emu):
+    """Single-pattern configs with aligned, 8-sample-multiple rows run entirely on the fast task
+    code; the default SEI (8 luma patterns) splits; ragged widths fall back to the general code."""
+    def mask_of(case, w, h):
+        meta = G.cases[case]
+        o = Oracle(); program_case(o, G, case)
+        frames = synth_frames(1, w, h, meta["fmt"], meta["depth"], seed=1)
+        return run_emu(emu, o, frames, 1, w, h, 0)[1]
+    assert mask_of("fgs_afgs1_test1.cfg|d10|420|g100", 512, 64) == 1
+    assert mask_of("fgs_sei_ff_test4.cfg|d10|444|g150", 512, 64) == 1
+    assert mask_of("fgs_sei_ff_test1.cfg|d8|420|g100", 512, 64) == 1
+    assert mask_of("fgs_sei.cfg|d10|420|g100", 512, 64) == 3
+    assert mask_of("fgs_afgs1_test1.cfg|d10|420|g100", 200, 64) == 3   # luma rows qualify, chroma width 100 does not
+    assert mask_of("fgs_afgs1_test1.cfg|d10|420|g100", 204, 64) == 2
+
+
+def test_fast_path_garbage_samples_and_minus_128(emu):
+    """10-bit containers holding out-of-range codes (up to 0xffff) clip like the reference's int
+    arithmetic; a pattern byte of -128 (cannot be negated in int8) must route to the general code."""
+    case = "fgs_afgs1_test1.cfg|d10|420|g100"
+    w, h, n = 512, 48, 1
+    rng = np.random.default_rng(5)
+    frames = rng.integers(0, 65536, size=w * h * 3 // 2, dtype=np.uint16)
+    o = Oracle(); program_case(o, G, case)
+    got, mask = run_emu(emu, o, frames, n, w, h, 0)
+    assert mask == 1 and np.array_equal(got, o.add_grain_frames(frames, n, w, h, 0))
+    st = G.state(case)
+    P = st["pattern"][0, 0].copy(); P[5, 7] = -128
+    o = Oracle(); program_case(o, G, case); o.vfgs_set_luma_pattern(0, np.ascontiguousarray(P))
+    frames = synth_frames(n, w, h, "420", 10, seed=2)
+    got, mask = run_emu(emu, o, frames, n, w, h, 0)
+    assert mask == 3 and np.array_equal(got, o.add_grain_frames(frames, n, w, h, 0))

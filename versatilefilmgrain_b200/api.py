@@ -27,6 +27,7 @@ B200_SYMBOLS = (
     "vfgs_b200_add_grain_frames_host", "vfgs_b200_skip_frames", "vfgs_b200_get_lfsr",
     "vfgs_b200_set_lfsr", "vfgs_b200_host_alloc", "vfgs_b200_host_free", "vfgs_b200_launch_count",
     "vfgs_b200_last_launch", "vfgs_b200_get_state", "vfgs_b200_kernel_timing", "vfgs_b200_kernel_time",
+    "vfgs_b200_force_general_kernel",
 )
 
 
@@ -88,6 +89,8 @@ def load_library(global_symbols: bool = False) -> C.CDLL:
     L.vfgs_b200_last_launch.restype = None
     L.vfgs_b200_kernel_timing.argtypes = [ci]
     L.vfgs_b200_kernel_time.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+    L.vfgs_b200_force_general_kernel.argtypes = [ci]
+    L.vfgs_b200_force_general_kernel.restype = None
     L.vfgs_b200_get_state.argtypes = [vp, C.c_size_t]
     L.vfgs_b200_get_state.restype = C.c_size_t
     _lib = L
@@ -140,6 +143,8 @@ class VfgsHw:
         ms, n = C.c_double(0), C.c_uint64(0)
         self._chk(self.L.vfgs_b200_kernel_time(C.byref(ms), C.byref(n)))
         return ms.value, int(n.value)
+
+    def force_general_kernel(self, on: bool): self.L.vfgs_b200_force_general_kernel(1 if on else 0)
 
     def last_launch(self) -> dict:
         a = (C.c_int * 4)()

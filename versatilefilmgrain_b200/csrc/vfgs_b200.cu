@@ -13,35 +13,13 @@
 #include "../../include/vfgs_b200.h"
 #include "../../include/vfgs_hw.h"
 #include "vfgs_kernels.cuh"
+#include "vfgs_tables.h"
 
 using namespace vfgs;
 
 namespace {
 
 // ------------------------------------------------------------------------------------ state
-constexpr int kSlots = 9; // 8 settable + the always-zero slot 8 (vfgs_hw.c:49)
-
-struct HwState {
-	int8_t pattern[2][kSlots][64][64];
-	uint8_t slut[3][256];
-	uint8_t plut[3][256];
-	uint32_t rnd, rnd_up, line_rnd, line_rnd_up;
-	int scale_shift, bs;
-	int y_min, y_max, c_min, c_max;
-	int csubx, csuby;
-	void power_on()
-	{
-		memset(pattern, 0, sizeof(pattern));
-		memset(slut, 0, sizeof(slut));
-		memset(plut, 0, sizeof(plut));
-		rnd = rnd_up = line_rnd = line_rnd_up = 0xdeadbeefu; // vfgs_hw.c:52-55
-		scale_shift = 5 + 6;                                 // vfgs_hw.c:56
-		bs = 0;
-		y_min = c_min = 0; y_max = c_max = 255;
-		csubx = csuby = 2;
-	}
-};
-
 struct Slot { // one stage of the host pipeline
 	uint8_t* d_in = nullptr;
 	uint8_t* d_out = nullptr;
@@ -59,6 +37,9 @@ struct Context {
 	uint32_t* d_pow2 = nullptr;
 	uint8_t* d_blob = nullptr;
 	size_t blob_cap = 0;
+	uint8_t* d_fblob = nullptr; // fast-path table image
+	size_t fblob_cap = 0;
+	int fast_smem_attr = 0;
 	uint32_t* d_streams = nullptr; // device entry point / line path
 	size_t streams_cap = 0;
 	cudaStream_t last_stream = nullptr;
@@ -82,10 +63,10 @@ bool g_hw_init = false;
 Context g_ctx;
 bool g_dirty = true; // table image must be rebuilt + uploaded
 std::vector<uint8_t> g_blob;
-struct BlobInfo {
-	int lut_off, pat_off[2], pat_size[2], pat_stride[2], uniform_pi[3], bytes;
-} g_bi;
+TableInfo g_bi;
+std::vector<uint8_t> g_fblob;
 uint64_t g_launches = 0;
+bool g_force_general = false; // test hook: route every component through the general kernel
 char g_err[512] = "";
 const JumpTable& jump_table()
 {
@@ -166,37 +147,7 @@ int grow(T*& p, size_t& cap, size_t need)
 }
 
 // ------------------------------------------------------------------------------------ table image
-// Layout (all offsets multiples of 16): LUT uint16[3][256] = scale | slot << 8, then the luma slots in
-// use (4096 B each), then the chroma slots in use packed to (64/csuby) rows x (64/csubx) bytes.
-void build_blob()
-{
-	const HwState& h = hw();
-	int nslot[2] = {1, 1};
-	for (int c = 0; c < 3; c++) {
-		int first = h.plut[c][0] >> 4, uni = first;
-		for (int i = 0; i < 256; i++) {
-			int s = h.plut[c][i] >> 4;
-			if (s != first) uni = -1;
-			if (s + 1 > nslot[c ? 1 : 0]) nslot[c ? 1 : 0] = s + 1;
-		}
-		g_bi.uniform_pi[c] = uni;
-	}
-	const int crows = 64 / h.csuby, ccols = 64 / h.csubx;
-	g_bi.lut_off = 0;
-	g_bi.pat_off[0] = 3 * 256 * 2;
-	g_bi.pat_size[0] = 64 * 64; g_bi.pat_stride[0] = 64;
-	g_bi.pat_off[1] = g_bi.pat_off[0] + nslot[0] * 4096;
-	g_bi.pat_size[1] = crows * ccols; g_bi.pat_stride[1] = ccols;
-	g_bi.bytes = (g_bi.pat_off[1] + nslot[1] * g_bi.pat_size[1] + 16 + 15) & ~15; // +16: fetch8 may touch one word past an octet
-	g_blob.assign((size_t)g_bi.bytes, 0);
-	uint16_t* lut = (uint16_t*)g_blob.data();
-	for (int c = 0; c < 3; c++)
-		for (int i = 0; i < 256; i++) lut[c * 256 + i] = (uint16_t)(h.slut[c][i] | ((h.plut[c][i] >> 4) << 8));
-	for (int s = 0; s < nslot[0]; s++) memcpy(&g_blob[g_bi.pat_off[0] + s * 4096], h.pattern[0][s], 4096);
-	for (int s = 0; s < nslot[1]; s++)
-		for (int r = 0; r < crows; r++)
-			memcpy(&g_blob[g_bi.pat_off[1] + s * g_bi.pat_size[1] + r * ccols], h.pattern[1][s][r], (size_t)ccols);
-}
+void build_blob() { build_tables(hw(), g_bi, g_blob, g_fblob); }
 
 int upload_blob()
 {
@@ -212,6 +163,15 @@ int upload_blob()
 	if (g_bi.bytes > c.smem_attr) {
 		CUDA_TRY(cudaFuncSetAttribute(fgs_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_bi.bytes));
 		c.smem_attr = g_bi.bytes;
+	}
+	if (int rc = grow(c.d_fblob, c.fblob_cap, (size_t)g_bi.fbytes)) return rc;
+	CUDA_TRY(cudaMemcpy(c.d_fblob, g_fblob.data(), (size_t)g_bi.fbytes, cudaMemcpyHostToDevice));
+	if (kLutBytes + g_bi.fbytes > c.fast_smem_attr) {
+		const int need = kLutBytes + g_bi.fbytes;
+		CUDA_TRY(cudaFuncSetAttribute(fgs_apply_fast_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
+		CUDA_TRY(cudaFuncSetAttribute(fgs_apply_fast_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
+		CUDA_TRY(cudaFuncSetAttribute(fgs_apply_fast_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
+		c.fast_smem_attr = need;
 	}
 	g_dirty = false;
 	return VFGS_B200_OK;
@@ -249,49 +209,34 @@ int make_geometry(Geometry& g, int width, int height, int out_depth)
 	return VFGS_B200_OK;
 }
 
-bool aligned_for(const void* base, long long row, long long frame, size_t unit)
-{
-	return ((uintptr_t)base % unit) == 0 && (row % (long long)unit) == 0 && (frame % (long long)unit) == 0;
-}
-
 void fill_common(FgsParams& p, const Geometry& g)
 {
-	const HwState& h = hw();
 	memset(&p, 0, sizeof(p));
+	fill_state_params(p, hw(), g_bi);
 	p.nb = g.nb; p.R = g.R;
-	p.subx = h.csubx; p.suby = h.csuby;
 	p.in_bytes = (int)g.in_sample; p.out_bytes = (int)g.out_sample;
-	p.bs = h.bs; p.ss = h.scale_shift;
-	for (int c = 0; c < 3; c++) {
-		p.lo[c] = (c ? h.c_min : h.y_min) << h.bs;
-		p.hi[c] = (c ? h.c_max : h.y_max) << h.bs;
-		p.uniform_pi[c] = g_bi.uniform_pi[c];
-	}
-	p.blob = g_ctx.d_blob; p.blob_bytes = g_bi.bytes;
-	p.lut_off = g_bi.lut_off;
-	for (int b = 0; b < 2; b++) { p.pat_off[b] = g_bi.pat_off[b]; p.pat_size[b] = g_bi.pat_size[b]; p.pat_stride[b] = g_bi.pat_stride[b]; }
+	p.blob = g_ctx.d_blob; p.fblob = g_ctx.d_fblob;
 	p.wpr = g.wpr;
 }
 
-void finish_tasks(FgsParams& p)
-{
-	for (int c = 0; c < 3; c++) {
-		p.nseg[c] = (p.comp[c].width + kSegSamples - 1) / kSegSamples;
-		p.comp[c].vec = aligned_for(p.comp[c].in, p.comp[c].in_row_bytes, p.in_frame_bytes, 8 * (size_t)p.in_bytes) &&
-		                aligned_for(p.comp[c].out, p.comp[c].out_row_bytes, p.out_frame_bytes, 8 * (size_t)p.out_bytes);
-	}
-	p.tasks_per_stripe = p.nseg[0] + p.nseg[1] + p.nseg[2];
-	p.total_tasks = (long long)p.nframes * p.rows * p.tasks_per_stripe;
-}
+typedef void (*GrainKernel)(const FgsParams);
 
-int launch_apply(const FgsParams& p, cudaStream_t stream)
+int launch_apply(const FgsParams& p, cudaStream_t stream, bool fast = false)
 {
 	Context& c = g_ctx;
 	if (p.total_tasks <= 0) return VFGS_B200_OK;
+	GrainKernel kern = fgs_apply_kernel;
+	int threads = kCtaThreads, smem = p.blob_bytes;
+	if (fast) {
+		kern = p.in_bytes == 1 ? fgs_apply_fast_kernel<false, false>
+		     : p.out_bytes == 1 ? fgs_apply_fast_kernel<true, true> : fgs_apply_fast_kernel<true, false>;
+		threads = kFastThreads; smem = kLutBytes + p.fblob_bytes;
+	}
+	const int wpc = threads / 32;
 	int per_sm = 0;
-	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fgs_apply_kernel, kCtaThreads, (size_t)p.blob_bytes));
-	if (per_sm < 1) return set_err(VFGS_B200_ERR_CUDA, "grain kernel does not fit on an SM (smem %d)", p.blob_bytes);
-	long long want = (p.total_tasks + kWarpsPerCta - 1) / kWarpsPerCta;
+	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, (size_t)smem));
+	if (per_sm < 1) return set_err(VFGS_B200_ERR_CUDA, "grain kernel does not fit on an SM (smem %d)", smem);
+	long long want = (p.total_tasks + wpc - 1) / wpc;
 	long long cap = (long long)c.sm_count * per_sm; // persistent grid: a whole number of CTAs per SM
 	int grid = (int)(want < cap ? want : cap);
 	cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -305,11 +250,11 @@ int launch_apply(const FgsParams& p, cudaStream_t stream)
 		e0 = c.ev_begin[c.ev_used]; e1 = c.ev_end[c.ev_used]; c.ev_used++;
 		CUDA_TRY(cudaEventRecord(e0, stream));
 	}
-	fgs_apply_kernel<<<grid, kCtaThreads, (size_t)p.blob_bytes, stream>>>(p);
+	kern<<<grid, threads, (size_t)smem, stream>>>(p);
 	CUDA_TRY(cudaGetLastError());
 	if (c.timing) CUDA_TRY(cudaEventRecord(e1, stream));
 	g_launches++;
-	c.last_launch[0] = grid; c.last_launch[1] = kCtaThreads; c.last_launch[2] = p.blob_bytes; c.last_launch[3] = c.sm_count;
+	c.last_launch[0] = grid; c.last_launch[1] = threads; c.last_launch[2] = smem; c.last_launch[3] = c.sm_count;
 	return VFGS_B200_OK;
 }
 
@@ -361,7 +306,15 @@ int run_frames_device(const vfgs_b200_planes& in, const vfgs_b200_planes& out, i
 	p.streams = d_streams; p.stream_rows = g.R; p.stream_row0 = 0;
 	finish_tasks(p);
 	if (int rc = launch_streams(epoch, d_streams, n, g, frame0, stream)) return rc;
-	return launch_apply(p, stream);
+	// components that qualify go through the fast kernel, the rest through the general one
+	FgsParams pf, pg;
+	bool any_fast, any_general;
+	split_fast_general(p, g_bi, g_force_general, pf, pg, any_fast, any_general);
+	if (any_fast)
+		if (int rc = launch_apply(pf, stream, true)) return rc;
+	if (any_general)
+		if (int rc = launch_apply(pg, stream, false)) return rc;
+	return VFGS_B200_OK;
 }
 
 void packed_planes(vfgs_b200_planes& pl, const void* base, const Geometry& g, size_t sample, size_t frame_bytes)
@@ -678,6 +631,8 @@ void vfgs_b200_host_free(void* p)
 }
 
 uint64_t vfgs_b200_launch_count(void) { return g_launches; }
+
+void vfgs_b200_force_general_kernel(int on) { g_force_general = on != 0; }
 
 int vfgs_b200_kernel_timing(int enable)
 {

@@ -148,6 +148,12 @@ struct FgsParams {
 	int pat_off[2];         // luma / chroma pattern slots
 	int pat_size[2];        // bytes per slot
 	int pat_stride[2];      // bytes per pattern row
+	// table image of the fast path (fgs_fast.h): uint32 lut[256] = sLUT[Y] | sLUT[U]<<8 | sLUT[V]<<16, then
+	// per component its single pattern slot twice (+pattern, -pattern)
+	const uint8_t* fblob;
+	int fblob_bytes;
+	int fpat_off[3][2];     // byte offsets inside the kernel's shared memory (after the expanded LUT)
+	int fpat_stride[3];
 	// LFSR bit-streams, one row of `wpr` words per (frame, block-row)
 	const uint32_t* streams;
 	int wpr, stream_rows, stream_row0;

@@ -12,7 +12,7 @@
 //                        loads and stores.
 #pragma once
 #include <cuda_runtime.h>
-#include "fgs_task.h"
+#include "fgs_fast.h"
 
 namespace vfgs {
 
@@ -95,6 +95,39 @@ fgs_apply_kernel(const __grid_constant__ FgsParams p)
 	const long long stride = (long long)gridDim.x * kWarpsPerCta;
 	for (long long task = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); task < p.total_tasks; task += stride)
 		process_task(p, tab, task, lane);
+}
+
+// Fast path: single-pattern components, aligned rows (fgs_fast.h). 512-thread persistent CTAs, two
+// per SM; shared memory = per-lane replicated scale LUT (32 KB, expanded here from the 1 KB compact
+// LUT) + the +/- pattern copies, brought in by one bulk async copy.
+constexpr int kFastThreads = 512;
+constexpr int kFastWarps = kFastThreads / 32;
+
+template <bool IN16, bool OUT8>
+__global__ void __launch_bounds__(kFastThreads, 2)
+fgs_apply_fast_kernel(const __grid_constant__ FgsParams p)
+{
+	extern __shared__ __align__(128) uint8_t smem[];
+	__shared__ __align__(8) uint64_t bar;
+
+	if (threadIdx.x == 0) mbar_init(&bar, 1);
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		mbar_arrive_expect_tx(&bar, (uint32_t)p.fblob_bytes);
+		bulk_copy_g2s(smem + kLutBytes, p.fblob, (uint32_t)p.fblob_bytes, &bar);
+	}
+	mbar_wait(&bar, 0);
+	{
+		const uint32_t* compact = (const uint32_t*)(smem + kLutBytes);
+		uint32_t* lut = (uint32_t*)smem;
+		for (int i = threadIdx.x; i < 256 * 32; i += kFastThreads) lut[i] = compact[i >> 5];
+	}
+	__syncthreads();
+
+	const int lane = threadIdx.x & 31;
+	const long long stride = (long long)gridDim.x * kFastWarps;
+	for (long long task = (long long)blockIdx.x * kFastWarps + (threadIdx.x >> 5); task < p.total_tasks; task += stride)
+		process_task_fast<IN16, OUT8>(p, smem, task, lane);
 }
 
 } // namespace vfgs

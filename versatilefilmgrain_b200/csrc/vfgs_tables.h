@@ -1,0 +1,161 @@
+// vfgs_tables.h -- host-side mirror of the hardware state and the construction of the table images
+// and launch parameters the kernels consume. Plain C++ (no CUDA runtime), shared by the C-ABI shim
+// (vfgs_b200.cu) and, for the GPU-less logic tests only, by tests/emu/emu.cpp.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+#include <vector>
+
+#include "fgs_fast.h"
+
+namespace vfgs {
+
+constexpr int kSlots = 9; // 8 settable + the always-zero slot 8 (vfgs_hw.c:49)
+
+struct HwState {
+	int8_t pattern[2][kSlots][64][64];
+	uint8_t slut[3][256];
+	uint8_t plut[3][256];
+	uint32_t rnd, rnd_up, line_rnd, line_rnd_up;
+	int scale_shift, bs;
+	int y_min, y_max, c_min, c_max;
+	int csubx, csuby;
+	void power_on()
+	{
+		memset(pattern, 0, sizeof(pattern));
+		memset(slut, 0, sizeof(slut));
+		memset(plut, 0, sizeof(plut));
+		rnd = rnd_up = line_rnd = line_rnd_up = 0xdeadbeefu; // vfgs_hw.c:52-55
+		scale_shift = 5 + 6;                                 // vfgs_hw.c:56
+		bs = 0;
+		y_min = c_min = 0; y_max = c_max = 255;
+		csubx = csuby = 2;
+	}
+};
+
+struct TableInfo {
+	// general image (fgs_task.h)
+	int lut_off, pat_off[2], pat_size[2], pat_stride[2], uniform_pi[3], bytes;
+	// fast image (fgs_fast.h): usable for a component when its pattern LUT selects one slot and that
+	// slot has no -128 byte (so that -pattern fits int8)
+	bool fast_ok[3];
+	int fpat_off[3][2], fpat_stride[3], fbytes;
+};
+
+// General image layout (all offsets multiples of 16): LUT uint16[3][256] = scale | slot << 8, then the
+// luma slots in use (4096 B each), then the chroma slots in use packed to (64/csuby) rows x (64/csubx) bytes.
+inline void build_tables(const HwState& h, TableInfo& g_bi, std::vector<uint8_t>& g_blob, std::vector<uint8_t>& g_fblob)
+{
+	int nslot[2] = {1, 1};
+	for (int c = 0; c < 3; c++) {
+		int first = h.plut[c][0] >> 4, uni = first;
+		for (int i = 0; i < 256; i++) {
+			int s = h.plut[c][i] >> 4;
+			if (s != first) uni = -1;
+			if (s + 1 > nslot[c ? 1 : 0]) nslot[c ? 1 : 0] = s + 1;
+		}
+		g_bi.uniform_pi[c] = uni;
+	}
+	const int crows = 64 / h.csuby, ccols = 64 / h.csubx;
+	g_bi.lut_off = 0;
+	g_bi.pat_off[0] = 3 * 256 * 2;
+	g_bi.pat_size[0] = 64 * 64; g_bi.pat_stride[0] = 64;
+	g_bi.pat_off[1] = g_bi.pat_off[0] + nslot[0] * 4096;
+	g_bi.pat_size[1] = crows * ccols; g_bi.pat_stride[1] = ccols;
+	g_bi.bytes = (g_bi.pat_off[1] + nslot[1] * g_bi.pat_size[1] + 16 + 15) & ~15; // +16: fetch8 may touch one word past an octet
+	g_blob.assign((size_t)g_bi.bytes, 0);
+	uint16_t* lut = (uint16_t*)g_blob.data();
+	for (int c = 0; c < 3; c++)
+		for (int i = 0; i < 256; i++) lut[c * 256 + i] = (uint16_t)(h.slut[c][i] | ((h.plut[c][i] >> 4) << 8));
+	for (int s = 0; s < nslot[0]; s++) memcpy(&g_blob[g_bi.pat_off[0] + s * 4096], h.pattern[0][s], 4096);
+	for (int s = 0; s < nslot[1]; s++)
+		for (int r = 0; r < crows; r++)
+			memcpy(&g_blob[g_bi.pat_off[1] + s * g_bi.pat_size[1] + r * ccols], h.pattern[1][s][r], (size_t)ccols);
+
+	// fast-path image: compact scale LUT, then +pattern / -pattern of each component's single slot
+	int off = 256 * 4;
+	for (int c = 0; c < 3; c++) {
+		const int rows = c ? crows : 64, cols = c ? ccols : 64;
+		const int slot = g_bi.uniform_pi[c];
+		bool ok = slot >= 0;
+		for (int r = 0; ok && r < rows; r++)
+			for (int x = 0; x < cols; x++)
+				if (h.pattern[c ? 1 : 0][slot][r][x] == -128) { ok = false; break; }
+		g_bi.fast_ok[c] = ok;
+		g_bi.fpat_stride[c] = cols;
+		g_bi.fpat_off[c][0] = kLutBytes + off;
+		g_bi.fpat_off[c][1] = kLutBytes + off + rows * cols;
+		off += 2 * rows * cols;
+	}
+	g_bi.fbytes = (off + 16 + 15) & ~15; // +16: the unaligned octet fetch may touch one word past a row
+	g_fblob.assign((size_t)g_bi.fbytes, 0);
+	uint32_t* clut = (uint32_t*)g_fblob.data();
+	for (int i = 0; i < 256; i++) clut[i] = (uint32_t)h.slut[0][i] | ((uint32_t)h.slut[1][i] << 8) | ((uint32_t)h.slut[2][i] << 16);
+	for (int c = 0; c < 3; c++) {
+		if (!g_bi.fast_ok[c]) continue;
+		const int rows = c ? crows : 64, cols = c ? ccols : 64;
+		int8_t* plus = (int8_t*)&g_fblob[g_bi.fpat_off[c][0] - kLutBytes];
+		int8_t* minus = (int8_t*)&g_fblob[g_bi.fpat_off[c][1] - kLutBytes];
+		for (int r = 0; r < rows; r++)
+			for (int x = 0; x < cols; x++) {
+				const int8_t v = h.pattern[c ? 1 : 0][g_bi.uniform_pi[c]][r][x];
+				plus[r * cols + x] = v; minus[r * cols + x] = (int8_t)-v;
+			}
+	}
+}
+
+
+// State- and table-dependent part of the launch parameters (pointers to the device copies of the
+// images are filled in by the caller).
+inline void fill_state_params(FgsParams& p, const HwState& h, const TableInfo& bi)
+{
+	p.subx = h.csubx; p.suby = h.csuby;
+	p.bs = h.bs; p.ss = h.scale_shift;
+	for (int c = 0; c < 3; c++) {
+		p.lo[c] = (c ? h.c_min : h.y_min) << h.bs;
+		p.hi[c] = (c ? h.c_max : h.y_max) << h.bs;
+		p.uniform_pi[c] = bi.uniform_pi[c];
+		p.fpat_off[c][0] = bi.fpat_off[c][0]; p.fpat_off[c][1] = bi.fpat_off[c][1];
+		p.fpat_stride[c] = bi.fpat_stride[c];
+	}
+	p.blob_bytes = bi.bytes; p.fblob_bytes = bi.fbytes;
+	p.lut_off = bi.lut_off;
+	for (int b = 0; b < 2; b++) { p.pat_off[b] = bi.pat_off[b]; p.pat_size[b] = bi.pat_size[b]; p.pat_stride[b] = bi.pat_stride[b]; }
+}
+
+inline bool aligned_for(const void* base, long long row, long long frame, size_t unit)
+{
+	return ((uintptr_t)base % unit) == 0 && (row % (long long)unit) == 0 && (frame % (long long)unit) == 0;
+}
+
+// Segments per line, vector-access eligibility and the task count, once planes and sizes are set.
+inline void finish_tasks(FgsParams& p)
+{
+	for (int c = 0; c < 3; c++) {
+		p.nseg[c] = (p.comp[c].width + kSegSamples - 1) / kSegSamples;
+		p.comp[c].vec = aligned_for(p.comp[c].in, p.comp[c].in_row_bytes, p.in_frame_bytes, 8 * (size_t)p.in_bytes) &&
+		                aligned_for(p.comp[c].out, p.comp[c].out_row_bytes, p.out_frame_bytes, 8 * (size_t)p.out_bytes);
+	}
+	p.tasks_per_stripe = p.nseg[0] + p.nseg[1] + p.nseg[2];
+	p.total_tasks = (long long)p.nframes * p.rows * p.tasks_per_stripe;
+}
+
+// Split a whole-frame launch between the fast kernel (components with one pattern slot, vector-
+// aligned rows, width % 8 == 0) and the general kernel. Returns {any_fast, any_general}.
+inline void split_fast_general(const FgsParams& p, const TableInfo& bi, bool force_general, FgsParams& pf, FgsParams& pg,
+                               bool& any_fast, bool& any_general)
+{
+	pf = p; pg = p;
+	any_fast = any_general = false;
+	for (int c = 0; c < 3; c++) {
+		const bool fast = bi.fast_ok[c] && p.comp[c].vec && (p.comp[c].width % kSamplesPerLane) == 0 && !force_general;
+		(fast ? pg : pf).nseg[c] = 0;
+		(fast ? any_fast : any_general) = true;
+	}
+	for (FgsParams* q : {&pf, &pg}) {
+		q->tasks_per_stripe = q->nseg[0] + q->nseg[1] + q->nseg[2];
+		q->total_tasks = (long long)q->nframes * q->rows * q->tasks_per_stripe;
+	}
+}
+
+} // namespace vfgs

@@ -13,10 +13,11 @@ echo "smoke rc=$?"; tail -3 gpurun_out/smoke.log
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest rc=$?"; tail -15 gpurun_out/pytest_gpu.log
 
-WL="${WORKLOADS:-4k420_afgs1_10to10}"
-for wl in $WL; do
-  timeout 900 python bench.py --steps 20 --warmup 5 --workload "$wl" > "gpurun_out/bench_$wl.log" 2>&1
-  echo "bench $wl rc=$?"; tail -1 "gpurun_out/bench_$wl.log"
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_4k420_afgs1_10to10.log 2>&1
+echo "bench rc=$?"; tail -1 gpurun_out/bench_4k420_afgs1_10to10.log
+for wl in ${WORKLOADS:-}; do
+  timeout 900 python bench.py --steps 20 --warmup 5 --workload "$wl" --no-cpu-baseline > "gpurun_out/bench_$wl.log" 2>&1
+  echo "bench $wl rc=$?"; tail -1 "gpurun_out/bench_$wl.log" | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['config']['name'], round(d['value']), 'fps', round(d['roofline']['achieved']), 'GB/s', round(d['roofline']['frac'],3), 'e2e', round(d['e2e']['value']))"
 done
 
 if [ "${NCU:-1}" = "1" ]; then

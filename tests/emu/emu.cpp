@@ -23,10 +23,10 @@ struct StateDump { // == refh_state / oracle_dump
 };
 
 template <bool IN16, bool OUT8>
-void run_fast(const FgsParams& p, const uint8_t* smem)
+void run_fast(const FgsParams& p, const uint8_t* lut, const uint8_t* img)
 {
 	for (long long task = 0; task < p.total_tasks; task++)
-		for (int lane = 0; lane < 32; lane++) process_task_fast<IN16, OUT8>(p, smem, task, lane);
+		for (int lane = 0; lane < 32; lane++) process_task_fast<IN16, OUT8>(p, smem_addr(lut), smem_addr(img), (uint32_t)task, lane);
 }
 } // namespace
 
@@ -52,7 +52,7 @@ extern "C" int emu_add_grain_frames(const void* state, const void* in, void* out
 	const int in_depth = 8 + h.bs;
 	if (!out_depth) out_depth = in_depth;
 	const int cw = width / h.csubx, ch = height / h.csuby;
-	const int nb = (width + 15) / 16, R = (height + 15) / 16, wpr = ((nb + 31) >> 5) + 3;
+	const int nb = (width + 15) / 16, R = (height + 15) / 16, spitch = nb + 2;
 	const size_t isz = in_depth > 8 ? 2 : 1, osz = out_depth > 8 ? 2 : 1;
 	const size_t ysam = (size_t)width * height, csam = (size_t)cw * ch;
 
@@ -60,21 +60,23 @@ extern "C" int emu_add_grain_frames(const void* state, const void* in, void* out
 	std::vector<uint8_t> blob, fblob;
 	build_tables(h, bi, blob, fblob);
 
-	// "shared memory" of the two kernels
-	std::vector<uint32_t> tab_store((blob.size() + 64) / 4), smem_store((kLutBytes + fblob.size() + 64) / 4);
+	// "shared memory" of the two kernels (the fast kernel's LUT on a 32 KB boundary, like on the device)
+	std::vector<uint32_t> tab_store((blob.size() + 64) / 4);
 	uint8_t* tab = (uint8_t*)tab_store.data();
 	memcpy(tab, blob.data(), blob.size());
-	uint8_t* smem = (uint8_t*)smem_store.data();
-	memcpy(smem + kLutBytes, fblob.data(), fblob.size());
-	for (int i = 0; i < 256 * 32; i++) ((uint32_t*)smem)[i] = ((const uint32_t*)(smem + kLutBytes))[i >> 5];
+	std::vector<uint8_t> smem_store((size_t)kLutAlign + kLutBytes + fblob.size() + 64);
+	uint8_t* lut_ptr = (uint8_t*)(((uintptr_t)smem_store.data() + kLutAlign - 1) & ~(uintptr_t)(kLutAlign - 1));
+	uint8_t* img_ptr = lut_ptr + kLutBytes;
+	memcpy(img_ptr, fblob.data(), fblob.size());
+	for (int i = 0; i < 256 * 32; i++) ((uint32_t*)lut_ptr)[i] = ((const uint32_t*)img_ptr)[i >> 5];
 
-	// LFSR streams (what lfsr_streams_kernel produces)
-	std::vector<uint32_t> streams((size_t)nframes * R * wpr);
+	// per-block LFSR registers (what lfsr_states_kernel produces)
+	std::vector<uint32_t> states((size_t)nframes * R * spitch, 0);
 	for (int f = 0; f < nframes; f++)
 		for (int r = 0; r < R; r++) {
 			uint64_t t = ((uint64_t)(first_frame_index + f) * (uint64_t)(R - 1) + (uint64_t)r) * (uint64_t)nb;
 			uint32_t s = jt.jump(h.line_rnd, t);
-			for (int w = 0; w < wpr; w++) { streams[((size_t)f * R + r) * wpr + w] = s; s = jt.jump(s, 32); }
+			for (int b = 0; b < nb; b++) { states[((size_t)f * R + r) * spitch + 1 + b] = s; s = lfsr_step(s); }
 		}
 
 	FgsParams p;
@@ -94,19 +96,19 @@ extern "C" int emu_add_grain_frames(const void* state, const void* in, void* out
 		p.comp[c].width = c ? cw : width;
 		p.comp[c].lines = c ? ch : height;
 	}
-	p.streams = streams.data(); p.wpr = wpr; p.stream_rows = R; p.stream_row0 = 0;
+	p.states = states.data(); p.spitch = spitch; p.stream_rows = R; p.stream_row0 = 0;
 	finish_tasks(p);
 
 	FgsParams pf, pg;
 	bool any_fast, any_general;
 	split_fast_general(p, bi, force_general != 0, pf, pg, any_fast, any_general);
 	if (any_fast) {
-		if (isz == 1) run_fast<false, false>(pf, smem);
-		else if (osz == 1) run_fast<true, true>(pf, smem);
-		else run_fast<true, false>(pf, smem);
+		if (isz == 1) run_fast<false, false>(pf, lut_ptr, img_ptr);
+		else if (osz == 1) run_fast<true, true>(pf, lut_ptr, img_ptr);
+		else run_fast<true, false>(pf, lut_ptr, img_ptr);
 	}
 	if (any_general)
 		for (long long task = 0; task < pg.total_tasks; task++)
-			for (int lane = 0; lane < 32; lane++) process_task(pg, tab, task, lane);
+			for (int lane = 0; lane < 32; lane++) process_task(pg, tab, (uint32_t)task, lane);
 	return (any_fast ? 1 : 0) | (any_general ? 2 : 0);
 }

@@ -91,26 +91,69 @@ VFGS_HD uint32_t min_u16x2(uint32_t a, uint32_t b)
 #endif
 }
 
+VFGS_HD uint32_t mulhi_u32(uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+	return __umulhi(a, b);
+#else
+	return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+
 // ---- shared-memory image of the fast path --------------------------------------------------
-// [0, kLutBytes)            uint32 lut[256][32]   per-lane replicated scale LUT (built by the CTA)
-// [kLutBytes, +fblob_bytes) copy of the global image: uint32 compact_lut[256], then for each component
-//                           its pattern slot twice (+ and -), rows packed to fpat_stride bytes
+//   lut   uint32 lut[256][32], per-lane replicated scale LUT (built by the CTA), placed on a 32 KB
+//         boundary of the shared window so that "lane column | index bits" is a plain OR
+//   img   copy of the global image: uint32 compact_lut[256], then for each component its pattern slot
+//         twice (+ and -), rows packed to fpat_stride bytes; fpat_off is relative to img
+// Addresses are absolute: 32-bit shared-window addresses on the device, pointers in the host build.
 constexpr int kLutBytes = 256 * 32 * 4;
+constexpr int kLutAlign = 32768;
 
-VFGS_HD uint32_t lds32(const uint8_t* smem, int off) { return *(const uint32_t*)(smem + off); }
-VFGS_HD int lds_s8(const uint8_t* smem, int off) { return (int)(int8_t)smem[off]; }
-VFGS_HD int lds_u8(const uint8_t* smem, int off) { return (int)smem[off]; }
+#if defined(__CUDA_ARCH__)
+typedef uint32_t smem_addr_t;
+__device__ __forceinline__ smem_addr_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds32(smem_addr_t a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ int lds_s8(smem_addr_t a) { int v; asm("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ int lds_u8(smem_addr_t a) { int v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+#else
+typedef uintptr_t smem_addr_t;
+inline smem_addr_t smem_addr(const void* p) { return (uintptr_t)p; }
+inline uint32_t lds32(smem_addr_t a) { return *(const uint32_t*)a; }
+inline int lds_s8(smem_addr_t a) { return (int)*(const int8_t*)a; }
+inline int lds_u8(smem_addr_t a) { return (int)*(const uint8_t*)a; }
+#endif
 
-// 8 consecutive pattern bytes at byte offset `off`; ALIGNED: off % 4 == 0 (luma-type components),
-// else off % 4 in {0, 2} (horizontally subsampled chroma: ox is a multiple of 2).
+// global load that only happens when pred is set; the destination keeps its value otherwise
+VFGS_HD void ld_global_16_if(const uint8_t* p, uint32_t r[4], bool pred)
+{
+#if defined(__CUDA_ARCH__)
+	asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];\n\t}"
+	             : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]) : "l"(p), "r"((uint32_t)pred));
+#else
+	if (pred) memcpy(r, p, 16);
+#endif
+}
+VFGS_HD void ld_global_8_if(const uint8_t* p, uint32_t r[2], bool pred)
+{
+#if defined(__CUDA_ARCH__)
+	asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q ld.global.L1::no_allocate.v2.u32 {%0,%1}, [%2];\n\t}"
+	             : "+r"(r[0]), "+r"(r[1]) : "l"(p), "r"((uint32_t)pred));
+#else
+	if (pred) memcpy(r, p, 8);
+#endif
+}
+
+// 8 consecutive pattern bytes at address a; ALIGNED: a % 4 == 0 (luma-type components), else
+// a % 4 in {0, 2} (horizontally subsampled chroma: ox is a multiple of 2).
 template <bool ALIGNED>
-VFGS_HD void octet(const uint8_t* smem, int off, uint32_t& w0, uint32_t& w1)
+VFGS_HD void octet(smem_addr_t a, uint32_t& w0, uint32_t& w1)
 {
 	if (ALIGNED) {
-		w0 = lds32(smem, off); w1 = lds32(smem, off + 4);
+		w0 = lds32(a); w1 = lds32(a + 4);
 	} else {
-		const int a = off & ~3, sh = (off & 3) * 8;
-		const uint32_t x0 = lds32(smem, a), x1 = lds32(smem, a + 4), x2 = lds32(smem, a + 8);
+		const smem_addr_t al = a & ~(smem_addr_t)3;
+		const int sh = (int)(a & 3) * 8;
+		const uint32_t x0 = lds32(al), x1 = lds32(al + 4), x2 = lds32(al + 8);
 #if defined(__CUDA_ARCH__)
 		w0 = __funnelshift_r(x0, x1, sh); w1 = __funnelshift_r(x1, x2, sh);
 #else
@@ -120,19 +163,19 @@ VFGS_HD void octet(const uint8_t* smem, int off, uint32_t& w0, uint32_t& w1)
 	}
 }
 
-// Per-lane constants of a warp-task (pattern byte offsets have the block's sign folded in).
+// Per-lane constants of a warp-task (pattern addresses have the block's sign folded in).
 struct FastLane {
-	int own;                 // the lane's octet, pattern row of line j = 0 of the current block
-	int lh, rh;              // halo bytes: last column of block b-1 / first column of block b+1
+	smem_addr_t own;         // the lane's octet, pattern row of line j = 0 of the current block
+	smem_addr_t lh, rh;      // halo bytes: last column of block b-1 / first column of block b+1
+	smem_addr_t lut;         // this lane's LUT column + component byte (index bits 7..14 are zero)
 	int stride;              // pattern row pitch
-	int lut;                 // byte offset of this lane's LUT column + component byte
 	bool has_left, has_right;
-	int ss, rnd;
-	uint32_t lo2, hi2;       // clip range replicated in both 16-bit halves (8-bit input: plain ints)
+	int pow16;               // 1 << (16 - scale_shift): products land in the upper half-word
+	uint32_t lo2, hi2;       // clip range replicated in both 16-bit halves
 };
-// Same offsets for the block-row above, only alive while the overlap lines are processed.
+// Same addresses for the block-row above, only alive while the overlap lines are processed.
 struct FastUp {
-	int own, lh, rh;
+	smem_addr_t own, lh, rh;
 };
 
 template <int E>
@@ -146,28 +189,28 @@ VFGS_HD int blend(int cur, uint32_t u0, uint32_t u1, int w_cur, int w_up) // vfg
 // rc: byte offset of this line's row inside the current block's window; w_cur != 0 selects the
 // vertical-overlap blend with row offset ru of the upper block's window.
 template <bool IN16, bool OUT8, int NSH>
-VFGS_HD void fast_line(const FastLane& L, const uint8_t* smem, int rc, int w_cur, int w_up, const FastUp& U, int ru,
+VFGS_HD void fast_line(const FastLane& L, int rc, int w_cur, int w_up, const FastUp& U, int ru,
                        const uint32_t raw[4], uint32_t outw[4])
 {
 	constexpr bool ALIGNED = NSH == 4;
 	uint32_t c0, c1;
-	octet<ALIGNED>(smem, L.own + rc, c0, c1);
+	octet<ALIGNED>(L.own + rc, c0, c1);
 	int g[8];
 	g[0] = octet_byte<0>(c0, c1); g[1] = octet_byte<1>(c0, c1); g[2] = octet_byte<2>(c0, c1); g[3] = octet_byte<3>(c0, c1);
 	g[4] = octet_byte<4>(c0, c1); g[5] = octet_byte<5>(c0, c1); g[6] = octet_byte<6>(c0, c1); g[7] = octet_byte<7>(c0, c1);
-	int hl = L.has_left ? lds_s8(smem, L.lh + rc) : 0;
-	int hr = L.has_right ? lds_s8(smem, L.rh + rc) : 0;
+	int hl = L.has_left ? lds_s8(L.lh + rc) : 0;
+	int hr = L.has_right ? lds_s8(L.rh + rc) : 0;
 
 	// vertical overlap with the block-row above (vfgs_hw.c:173-188, 223-229)
 	if (w_cur) {
 		uint32_t u0, u1;
-		octet<ALIGNED>(smem, U.own + ru, u0, u1);
+		octet<ALIGNED>(U.own + ru, u0, u1);
 		g[0] = blend<0>(g[0], u0, u1, w_cur, w_up); g[1] = blend<1>(g[1], u0, u1, w_cur, w_up);
 		g[2] = blend<2>(g[2], u0, u1, w_cur, w_up); g[3] = blend<3>(g[3], u0, u1, w_cur, w_up);
 		g[4] = blend<4>(g[4], u0, u1, w_cur, w_up); g[5] = blend<5>(g[5], u0, u1, w_cur, w_up);
 		g[6] = blend<6>(g[6], u0, u1, w_cur, w_up); g[7] = blend<7>(g[7], u0, u1, w_cur, w_up);
-		if (L.has_left) hl = (hl * w_cur + lds_s8(smem, U.lh + ru) * w_up + 16) >> 5;
-		if (L.has_right) hr = (hr * w_cur + lds_s8(smem, U.rh + ru) * w_up + 16) >> 5;
+		if (L.has_left) hl = (hl * w_cur + lds_s8(U.lh + ru) * w_up + 16) >> 5;
+		if (L.has_right) hr = (hr * w_cur + lds_s8(U.rh + ru) * w_up + 16) >> 5;
 	}
 
 	// block-edge filter (vfgs_hw.c:250-259), taps read unfiltered grain
@@ -176,16 +219,18 @@ VFGS_HD void fast_line(const FastLane& L, const uint8_t* smem, int rc, int w_cur
 	g[0] = L.has_left ? f0 : g[0];
 	g[7] = L.has_right ? f7 : g[7];
 
+	// scale * grain, rounded shift (vfgs_hw.c:263): with the grain pre-multiplied by 2^(16 - shift)
+	// the rounded quotient is exactly the upper half-word of scale * grain' + 0x8000
 	if (IN16) {
 		uint32_t r[4];
 #pragma unroll
 		for (int k = 0; k < 4; k++) {
 			// LUT index = (sample >> 2) & 0xff (vfgs_hw.c:211), times the 128-byte LUT row pitch
-			const int s_lo = lds_u8(smem, L.lut + (int)((raw[k] << 5) & 0x7f80u));
-			const int s_hi = lds_u8(smem, L.lut + (int)((raw[k] >> 11) & 0x7f80u));
-			const int d_lo = (s_lo * g[2 * k] + L.rnd) >> L.ss;      // vfgs_hw.c:263
-			const int d_hi = (s_hi * g[2 * k + 1] + L.rnd) >> L.ss;
-			const uint32_t d2 = prmt((uint32_t)d_lo, (uint32_t)d_hi, 0x5410);
+			const int s_lo = lds_u8(L.lut | (smem_addr_t)((raw[k] << 5) & 0x7f80u));
+			const int s_hi = lds_u8(L.lut | (smem_addr_t)(mulhi_u32(raw[k], 1u << 21) & 0x7f80u)); // raw >> 11 on the FMA pipe
+			const int a_lo = s_lo * (g[2 * k] * L.pow16) + 0x8000;
+			const int a_hi = s_hi * (g[2 * k + 1] * L.pow16) + 0x8000;
+			const uint32_t d2 = prmt((uint32_t)a_lo, (uint32_t)a_hi, 0x7632);
 			// samples above 0x3fff clip to the ceiling whatever the grain: cap them so the signed 16-bit add cannot wrap
 			const uint32_t v2 = min_u16x2(raw[k], 0x3fff3fffu);
 			r[k] = min_s16x2(add_max_s16x2(v2, d2, L.lo2), L.hi2);  // vfgs_hw.c:265
@@ -203,9 +248,12 @@ VFGS_HD void fast_line(const FastLane& L, const uint8_t* smem, int rc, int w_cur
 		int o[8];
 #pragma unroll
 		for (int e = 0; e < 8; e++) {
-			const int v = (int)((raw[e >> 2] >> ((e & 3) * 8)) & 0xff);
-			const int s = lds_u8(smem, L.lut + (v << 7));
-			int x = v + ((s * g[e] + L.rnd) >> L.ss);
+			const uint32_t word = raw[e >> 2];
+			const int sh = (e & 3) * 8;
+			const int v = (int)((word >> sh) & 0xff);
+			const uint32_t ibits = sh >= 7 ? (word >> (sh - 7)) & 0x7f80u : (word << (7 - sh)) & 0x7f80u; // v * 128
+			const int s = lds_u8(L.lut | (smem_addr_t)ibits);
+			int x = v + ((s * (g[e] * L.pow16) + 0x8000) >> 16);
 			x = x > hi ? hi : x;
 			o[e] = x < lo ? lo : x;
 		}
@@ -214,46 +262,17 @@ VFGS_HD void fast_line(const FastLane& L, const uint8_t* smem, int rc, int w_cur
 	}
 }
 
-// Pattern byte offset of (block window, column) inside the shared image.
-VFGS_HD int window_off(const FgsParams& p, int c, const BlockOfs& o, int col)
+// Address of (block window, column) inside the shared image.
+VFGS_HD smem_addr_t window_addr(const FgsParams& p, smem_addr_t img, int c, uint32_t state, int col)
 {
-	return p.fpat_off[c][o.sign < 0 ? 1 : 0] + o.oy * p.fpat_stride[c] + o.ox + col;
+	const BlockOfs o = decode_offsets(c, state, p.subx, p.suby);
+	return img + (smem_addr_t)(p.fpat_off[c][o.sign < 0 ? 1 : 0] + o.oy * p.fpat_stride[c] + o.ox + col);
 }
 
-constexpr int kFastLB = 4; // lines whose loads are issued back to back
-
-// kFastLB consecutive lines of the component (nl of them exist). ovl: this is the first batch of a
-// stripe that has a block-row above it: line 0 (and line 1 when the component is not vertically
-// subsampled) blend with the upper block's window U.
-template <bool IN16, bool OUT8, int NSH>
-VFGS_HD void fast_batch(const FastLane& L, const FastUp& U, const uint8_t* smem, int rc0, int ysh, bool ovl,
-                        const uint8_t* src, uint8_t* dst, long long in_pitch, long long out_pitch, int nl)
-{
-	constexpr int OB = (IN16 && !OUT8) ? 2 : 1;
-	uint32_t raw[kFastLB][4];
-#pragma unroll
-	for (int q = 0; q < kFastLB; q++) {
-		// a short last batch re-reads its last line instead of branching around the load
-		const int qq = q < nl ? q : nl - 1;
-		if (IN16) ld_global_16(src + qq * in_pitch, raw[q]);
-		else ld_global_8(src + qq * in_pitch, raw[q]);
-	}
-#pragma unroll
-	for (int q = 0; q < kFastLB; q++) {
-		uint32_t w[4];
-		int w_cur = 0, w_up = 0, ru = 0;
-		if (q == 0 && ovl) { w_cur = ysh ? 20 : 12; w_up = ysh ? 20 : 24; ru = (16 >> ysh) * L.stride; }
-		if (q == 1 && ovl && !ysh) { w_cur = 24; w_up = 12; ru = 17 * L.stride; }
-		fast_line<IN16, OUT8, NSH>(L, smem, rc0 + q * L.stride, w_cur, w_up, U, ru, raw[q], w);
-		if (q < nl) {
-			if (OB == 2) st_global_16(dst + q * out_pitch, w);
-			else st_global_8(dst + q * out_pitch, w);
-		}
-	}
-}
+constexpr int kFastLB = 4; // lines in flight per lane
 
 template <bool IN16, bool OUT8, int NSH>
-VFGS_HD void fast_task_body(const FgsParams& p, const uint8_t* smem, const TaskGeom& t, int lane)
+VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, smem_addr_t img, const TaskGeom& t, int lane)
 {
 	const int c = t.c;
 	const Plane& pl = p.comp[c];
@@ -267,7 +286,23 @@ VFGS_HD void fast_task_body(const FgsParams& p, const uint8_t* smem, const TaskG
 	const int cl0 = (t.r * 16) >> ysh;
 	int cl1 = cl0 + (16 >> ysh);
 	if (cl1 > pl.lines) cl1 = pl.lines;
-	if (cl0 >= cl1) return;
+	const int nl = cl1 - cl0;
+	if (nl <= 0) return;
+
+	constexpr int IB = IN16 ? 2 : 1, OB = (IN16 && !OUT8) ? 2 : 1;
+	const long long in_pitch = pl.in_row_bytes, out_pitch = pl.out_row_bytes;
+	const uint8_t* src = pl.in + (long long)t.f * p.in_frame_bytes + (long long)cl0 * in_pitch + (long long)k0 * IB;
+	uint8_t* dst = pl.out + (long long)t.f * p.out_frame_bytes + (long long)cl0 * out_pitch + (long long)k0 * OB;
+
+	// The first kFastLB lines are requested before anything else: the block decode below runs
+	// while they are in flight. A stripe shorter than kFastLB lines re-reads its last line.
+	uint32_t raw[kFastLB][4];
+#pragma unroll
+	for (int q = 0; q < kFastLB; q++) {
+		const int qq = q < nl ? q : nl - 1;
+		if (IN16) ld_global_16(src + qq * in_pitch, raw[q]);
+		else ld_global_8(src + qq * in_pitch, raw[q]);
+	}
 
 	const int b = k0 >> NSH;
 	const int i0 = k0 & (n - 1);
@@ -275,39 +310,49 @@ VFGS_HD void fast_task_body(const FgsParams& p, const uint8_t* smem, const TaskG
 	L.has_left = (i0 == 0) && (b > 0);
 	L.has_right = (i0 + kSamplesPerLane == n) && (b + 1 < p.nb);
 	L.stride = p.fpat_stride[c];
-	L.lut = lane * 4 + c;
-	L.ss = p.ss; L.rnd = 1 << (p.ss - 1);
+	L.lut = lut + (smem_addr_t)(lane * 4 + c);
+	L.pow16 = p.pow16;
 	L.lo2 = (uint32_t)p.lo[c] * 0x00010001u; L.hi2 = (uint32_t)p.hi[c] * 0x00010001u;
 
 	const int srow = t.r - p.stream_row0;
-	const uint32_t* row_cur = p.streams + ((long long)t.f * p.stream_rows + srow) * p.wpr;
-	L.own = window_off(p, c, decode_offsets(c, stream_window(row_cur, b), p.subx, p.suby), i0);
-	L.lh = L.rh = 0;
-	if (L.has_left) L.lh = window_off(p, c, decode_offsets(c, stream_window(row_cur, b - 1), p.subx, p.suby), n - 1);
-	if (L.has_right) L.rh = window_off(p, c, decode_offsets(c, stream_window(row_cur, b + 1), p.subx, p.suby), 0);
+	const uint32_t* row_cur = p.states + ((long long)t.f * p.stream_rows + srow) * p.spitch + 1 + b;
+	L.own = window_addr(p, img, c, row_cur[0], i0);
+	L.lh = L.rh = L.own;
+	if (L.has_left) L.lh = window_addr(p, img, c, row_cur[-1], n - 1);
+	if (L.has_right) L.rh = window_addr(p, img, c, row_cur[1], 0);
 
-	constexpr int IB = IN16 ? 2 : 1, OB = (IN16 && !OUT8) ? 2 : 1;
-	const long long in_pitch = pl.in_row_bytes, out_pitch = pl.out_row_bytes;
-	const uint8_t* src = pl.in + (long long)t.f * p.in_frame_bytes + (long long)cl0 * in_pitch + (long long)k0 * IB;
-	uint8_t* dst = pl.out + (long long)t.f * p.out_frame_bytes + (long long)cl0 * out_pitch + (long long)k0 * OB;
-	int nl = cl1 - cl0;
-
-	// the first batch of a stripe overlaps the block-row above (never in the first stripe, y <= 15)
+	// the first lines of a stripe overlap the block-row above (never in the first stripe, y <= 15)
 	FastUp U;
-	U.own = U.lh = U.rh = 0;
+	U.own = U.lh = U.rh = L.own;
 	bool ovl = t.r > 0;
 	if (ovl) {
-		const uint32_t* row_up = row_cur - p.wpr;
-		U.own = window_off(p, c, decode_offsets(c, stream_window(row_up, b), p.subx, p.suby), i0);
-		if (L.has_left) U.lh = window_off(p, c, decode_offsets(c, stream_window(row_up, b - 1), p.subx, p.suby), n - 1);
-		if (L.has_right) U.rh = window_off(p, c, decode_offsets(c, stream_window(row_up, b + 1), p.subx, p.suby), 0);
+		const uint32_t* row_up = row_cur - p.spitch;
+		U.own = window_addr(p, img, c, row_up[0], i0);
+		if (L.has_left) U.lh = window_addr(p, img, c, row_up[-1], n - 1);
+		if (L.has_right) U.rh = window_addr(p, img, c, row_up[1], 0);
 	}
+
 	int rc = 0;
+	const uint8_t* nxt = src + kFastLB * in_pitch; // line whose load refills the slot just consumed
 #pragma unroll 1
-	for (; nl > 0; nl -= kFastLB) {
-		fast_batch<IN16, OUT8, NSH>(L, U, smem, rc, ysh, ovl, src, dst, in_pitch, out_pitch, nl);
-		src += kFastLB * in_pitch; dst += kFastLB * out_pitch;
-		rc += kFastLB * L.stride;
+	for (int base = 0; base < nl; base += kFastLB) {
+#pragma unroll
+		for (int q = 0; q < kFastLB; q++) {
+			const int line = base + q;
+			uint32_t w[4];
+			int w_cur = 0, w_up = 0, ru = 0;
+			if (q == 0 && ovl) { w_cur = ysh ? 20 : 12; w_up = ysh ? 20 : 24; ru = (16 >> ysh) * L.stride; }
+			if (q == 1 && ovl && !ysh) { w_cur = 24; w_up = 12; ru = 17 * L.stride; }
+			fast_line<IN16, OUT8, NSH>(L, rc, w_cur, w_up, U, ru, raw[q], w);
+			// this slot's registers are free again: request the line kFastLB further down
+			if (IN16) ld_global_16_if(nxt, raw[q], line + kFastLB < nl);
+			else ld_global_8_if(nxt, raw[q], line + kFastLB < nl);
+			if (line < nl) {
+				if (OB == 2) st_global_16(dst, w);
+				else st_global_8(dst, w);
+			}
+			rc += L.stride; nxt += in_pitch; dst += out_pitch;
+		}
 		ovl = false;
 	}
 }
@@ -315,11 +360,11 @@ VFGS_HD void fast_task_body(const FgsParams& p, const uint8_t* smem, const TaskG
 // Dispatch on the component's block size (16 samples: luma and non-subsampled chroma; 8: chroma
 // subsampled horizontally).
 template <bool IN16, bool OUT8>
-VFGS_HD void process_task_fast(const FgsParams& p, const uint8_t* smem, long long task, int lane)
+VFGS_HD void process_task_fast(const FgsParams& p, smem_addr_t lut, smem_addr_t img, uint32_t task, int lane)
 {
 	const TaskGeom t = decode_task(p, task);
-	if (t.c && p.subx > 1) fast_task_body<IN16, OUT8, 3>(p, smem, t, lane);
-	else fast_task_body<IN16, OUT8, 4>(p, smem, t, lane);
+	if (t.c && p.subx > 1) fast_task_body<IN16, OUT8, 3>(p, lut, img, t, lane);
+	else fast_task_body<IN16, OUT8, 4>(p, lut, img, t, lane);
 }
 
 } // namespace vfgs

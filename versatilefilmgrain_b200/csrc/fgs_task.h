@@ -99,13 +99,13 @@ struct TaskGeom {
 	int f, r, c, seg;
 };
 
-VFGS_HD TaskGeom decode_task(const FgsParams& p, long long task)
+VFGS_HD TaskGeom decode_task(const FgsParams& p, uint32_t task)
 {
 	TaskGeom g;
-	const long long fr = task / p.tasks_per_stripe;
-	int q = (int)(task - fr * p.tasks_per_stripe);
-	g.f = (int)(fr / p.rows);
-	g.r = p.row_begin + (int)(fr - (long long)g.f * p.rows);
+	const uint32_t fr = task / (uint32_t)p.tasks_per_stripe;
+	int q = (int)(task - fr * (uint32_t)p.tasks_per_stripe);
+	g.f = (int)(fr / (uint32_t)p.rows);
+	g.r = p.row_begin + (int)(fr - (uint32_t)g.f * (uint32_t)p.rows);
 	if (q < p.nseg[0]) { g.c = 0; g.seg = q; }
 	else if (q < p.nseg[0] + p.nseg[1]) { g.c = 1; g.seg = q - p.nseg[0]; }
 	else { g.c = 2; g.seg = q - p.nseg[0] - p.nseg[1]; }
@@ -199,7 +199,7 @@ VFGS_HD void lane_line(const LaneCtx& L, int y, int ysh, const int v[8], int vl,
 }
 
 // Whole warp-task for one lane.
-VFGS_HD void process_task(const FgsParams& p, const uint8_t* tab, long long task, int lane)
+VFGS_HD void process_task(const FgsParams& p, const uint8_t* tab, uint32_t task, int lane)
 {
 	const TaskGeom t = decode_task(p, task);
 	const Plane& pl = p.comp[t.c];
@@ -232,19 +232,19 @@ VFGS_HD void process_task(const FgsParams& p, const uint8_t* tab, long long task
 	L.has_left = (L.i0 == 0) && (b > 0);
 	L.has_right = (L.i0 + kSamplesPerLane == n) && (b + 1 < p.nb);
 
-	// LFSR windows of this block and its neighbours, current and upper block-row
+	// LFSR registers of this block and its neighbours, current and upper block-row
 	const int srow = t.r - p.stream_row0;
-	const uint32_t* row_cur = p.streams + ((long long)t.f * p.stream_rows + srow) * p.wpr;
-	const uint32_t* row_up = srow > 0 ? row_cur - p.wpr : row_cur; // only read when y > 15
-	L.cur = decode_offsets(c, stream_window(row_cur, b), p.subx, p.suby);
-	L.up = decode_offsets(c, stream_window(row_up, b), p.subx, p.suby);
+	const uint32_t* row_cur = p.states + ((long long)t.f * p.stream_rows + srow) * p.spitch + 1;
+	const uint32_t* row_up = srow > 0 ? row_cur - p.spitch : row_cur; // only read when y > 15
+	L.cur = decode_offsets(c, row_cur[b], p.subx, p.suby);
+	L.up = decode_offsets(c, row_up[b], p.subx, p.suby);
 	if (L.has_left) {
-		L.lcur = decode_offsets(c, stream_window(row_cur, b - 1), p.subx, p.suby);
-		L.lup = decode_offsets(c, stream_window(row_up, b - 1), p.subx, p.suby);
+		L.lcur = decode_offsets(c, row_cur[b - 1], p.subx, p.suby);
+		L.lup = decode_offsets(c, row_up[b - 1], p.subx, p.suby);
 	} else { L.lcur = L.cur; L.lup = L.up; }
 	if (L.has_right) {
-		L.rcur = decode_offsets(c, stream_window(row_cur, b + 1), p.subx, p.suby);
-		L.rup = decode_offsets(c, stream_window(row_up, b + 1), p.subx, p.suby);
+		L.rcur = decode_offsets(c, row_cur[b + 1], p.subx, p.suby);
+		L.rup = decode_offsets(c, row_up[b + 1], p.subx, p.suby);
 	} else { L.rcur = L.cur; L.rup = L.up; }
 
 	const uint8_t* fin = pl.in + (long long)t.f * p.in_frame_bytes;

@@ -166,8 +166,8 @@ int upload_blob()
 	}
 	if (int rc = grow(c.d_fblob, c.fblob_cap, (size_t)g_bi.fbytes)) return rc;
 	CUDA_TRY(cudaMemcpy(c.d_fblob, g_fblob.data(), (size_t)g_bi.fbytes, cudaMemcpyHostToDevice));
-	if (kLutBytes + g_bi.fbytes > c.fast_smem_attr) {
-		const int need = kLutBytes + g_bi.fbytes;
+	if (kLutAlign + kLutBytes + g_bi.fbytes > c.fast_smem_attr) {
+		const int need = kLutAlign + kLutBytes + g_bi.fbytes;
 		CUDA_TRY(cudaFuncSetAttribute(fgs_apply_fast_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
 		CUDA_TRY(cudaFuncSetAttribute(fgs_apply_fast_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
 		CUDA_TRY(cudaFuncSetAttribute(fgs_apply_fast_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
@@ -179,7 +179,7 @@ int upload_blob()
 
 // ------------------------------------------------------------------------------------ launch
 struct Geometry {
-	int width, height, cw, ch, nb, R, wpr;
+	int width, height, cw, ch, nb, R, spitch;
 	int in_depth, out_depth;
 	size_t in_sample, out_sample;
 	size_t ysam, csam;
@@ -201,7 +201,7 @@ int make_geometry(Geometry& g, int width, int height, int out_depth)
 	g.width = width; g.height = height;
 	g.cw = width / h.csubx; g.ch = height / h.csuby; // yuv.c:72-77
 	g.nb = (width + 15) / 16; g.R = (height + 15) / 16;
-	g.wpr = ((g.nb + 31) >> 5) + 3;
+	g.spitch = g.nb + 2;
 	g.in_sample = g.in_depth > 8 ? 2 : 1; g.out_sample = g.out_depth > 8 ? 2 : 1;
 	g.ysam = (size_t)width * height; g.csam = (size_t)g.cw * g.ch;
 	g.in_frame_bytes = (g.ysam + 2 * g.csam) * g.in_sample;
@@ -216,7 +216,7 @@ void fill_common(FgsParams& p, const Geometry& g)
 	p.nb = g.nb; p.R = g.R;
 	p.in_bytes = (int)g.in_sample; p.out_bytes = (int)g.out_sample;
 	p.blob = g_ctx.d_blob; p.fblob = g_ctx.d_fblob;
-	p.wpr = g.wpr;
+	p.spitch = g.spitch;
 }
 
 typedef void (*GrainKernel)(const FgsParams);
@@ -225,12 +225,13 @@ int launch_apply(const FgsParams& p, cudaStream_t stream, bool fast = false)
 {
 	Context& c = g_ctx;
 	if (p.total_tasks <= 0) return VFGS_B200_OK;
+	if (p.total_tasks >= (1ll << 31)) return set_err(VFGS_B200_ERR_ARG, "batch too large for one launch (%lld warp-tasks): split the call", p.total_tasks);
 	GrainKernel kern = fgs_apply_kernel;
 	int threads = kCtaThreads, smem = p.blob_bytes;
 	if (fast) {
 		kern = p.in_bytes == 1 ? fgs_apply_fast_kernel<false, false>
 		     : p.out_bytes == 1 ? fgs_apply_fast_kernel<true, true> : fgs_apply_fast_kernel<true, false>;
-		threads = kFastThreads; smem = kLutBytes + p.fblob_bytes;
+		threads = kFastThreads; smem = kLutAlign + kLutBytes + p.fblob_bytes; // slack to place the LUT on a 32 KB boundary
 	}
 	const int wpc = threads / 32;
 	int per_sm = 0;
@@ -262,7 +263,7 @@ int launch_streams(uint32_t epoch, uint32_t* d_streams, int nframes, const Geome
 {
 	const long long warps = (long long)nframes * g.R;
 	const int grid = (int)((warps * 32 + kCtaThreads - 1) / kCtaThreads);
-	lfsr_streams_kernel<<<grid, kCtaThreads, 0, stream>>>(epoch, g_ctx.d_pow2, d_streams, nframes, g.R, g.nb, g.wpr, frame0);
+	lfsr_states_kernel<<<grid, kCtaThreads, 0, stream>>>(epoch, g_ctx.d_pow2, d_streams, nframes, g.R, g.nb, g.spitch, frame0);
 	CUDA_TRY(cudaGetLastError());
 	g_launches++;
 	return VFGS_B200_OK;
@@ -303,7 +304,7 @@ int run_frames_device(const vfgs_b200_planes& in, const vfgs_b200_planes& out, i
 		p.comp[c].width = c ? g.cw : g.width;
 		p.comp[c].lines = c ? g.ch : g.height;
 	}
-	p.streams = d_streams; p.stream_rows = g.R; p.stream_row0 = 0;
+	p.states = d_streams; p.stream_rows = g.R; p.stream_row0 = 0;
 	finish_tasks(p);
 	if (int rc = launch_streams(epoch, d_streams, n, g, frame0, stream)) return rc;
 	// components that qualify go through the fast kernel, the rest through the general one
@@ -423,12 +424,12 @@ void vfgs_add_grain_line(void* Y, void* U, void* V, int y, int width)
 
 	if (y && (y & 15) == 0) { h.line_rnd_up = h.line_rnd; h.line_rnd = h.rnd; }
 
-	// two stream rows (upper, current) generated on the host: nb + a few words, trivial
-	std::vector<uint32_t> rows((size_t)2 * g.wpr);
+	// two rows of per-block registers (upper, current) stepped on the host: nb steps, trivial
+	std::vector<uint32_t> rows((size_t)2 * g.spitch, 0);
 	uint32_t su = h.line_rnd_up, sc = h.line_rnd;
-	for (int w = 0; w < g.wpr; w++) {
-		rows[w] = su; rows[(size_t)g.wpr + w] = sc;
-		su = jt.jump(su, 32); sc = jt.jump(sc, 32);
+	for (int b = 0; b < g.nb; b++) {
+		rows[1 + b] = su; rows[(size_t)g.spitch + 1 + b] = sc;
+		su = lfsr_step(su); sc = lfsr_step(sc);
 	}
 	const bool chroma = !((y & 1) && h.csuby > 1); // vfgs_hw.c:164-165
 	const size_t lbytes = (size_t)width * g.in_sample, cbytes = (size_t)g.cw * g.in_sample;
@@ -459,7 +460,7 @@ void vfgs_add_grain_line(void* Y, void* U, void* V, int y, int width)
 		p.comp[k].width = k ? g.cw : width;
 		p.comp[k].lines = (k && !chroma) ? 0 : 0x7fffffff;
 	}
-	p.streams = c.d_streams; p.stream_rows = 2; p.stream_row0 = (y >> 4) - 1;
+	p.states = c.d_streams; p.stream_rows = 2; p.stream_row0 = (y >> 4) - 1;
 	finish_tasks(p);
 	if (launch_apply(p, st)) fatal("vfgs_add_grain_line");
 	chk(cudaMemcpyAsync(Y, c.d_line, lbytes, cudaMemcpyDeviceToHost, st), "Y D2H");
@@ -507,7 +508,7 @@ int vfgs_b200_add_grain_planes_device(const vfgs_b200_planes* in, const vfgs_b20
 	cudaStream_t st = (cudaStream_t)stream;
 	if (c.used_stream && c.last_stream != st) CUDA_TRY(cudaStreamSynchronize(c.last_stream)); // d_streams is shared
 	c.last_stream = st; c.used_stream = true;
-	if (int rc = grow(c.d_streams, c.streams_cap, (size_t)nframes * g.R * g.wpr * sizeof(uint32_t))) return rc;
+	if (int rc = grow(c.d_streams, c.streams_cap, (size_t)nframes * g.R * g.spitch * sizeof(uint32_t))) return rc;
 	if (int rc = run_frames_device(*in, *out, nframes, g, hw().line_rnd, 0, c.d_streams, st)) return rc;
 	advance_registers(g, (uint64_t)nframes);
 	return VFGS_B200_OK;
@@ -549,7 +550,7 @@ int vfgs_b200_add_grain_frames_host(const void* in, void* out, int nframes, int 
 		Slot& s = c.slot[idx % kPipeSlots];
 		if (int rc = grow(s.d_in, s.in_cap, (size_t)per * g.in_frame_bytes)) return rc;
 		if (int rc = grow(s.d_out, s.out_cap, (size_t)per * g.out_frame_bytes)) return rc;
-		if (int rc = grow(s.d_streams, s.streams_cap, (size_t)per * g.R * g.wpr * sizeof(uint32_t))) return rc;
+		if (int rc = grow(s.d_streams, s.streams_cap, (size_t)per * g.R * g.spitch * sizeof(uint32_t))) return rc;
 		// the slot's previous chunk must have left the device before its buffers are overwritten
 		if (idx >= kPipeSlots) {
 			CUDA_TRY(cudaStreamWaitEvent(c.s_h2d, s.k_done, 0));   // d_in free once its kernel is done

@@ -131,13 +131,14 @@ constexpr int kSegSamples = 32 * kSamplesPerLane; // one warp-task covers 256 sa
 struct FgsParams {
 	Plane comp[3];
 	long long in_frame_bytes, out_frame_bytes;
-	long long total_tasks;
+	long long total_tasks;  // < 2^31 (the host splits larger batches)
 	int nframes, nb, R;
 	int row_begin, rows;    // block-rows [row_begin, row_begin + rows) of every frame carry tasks
 	int y_begin, y_end;     // luma line range to process inside each frame
 	int subx, suby;         // chroma subsampling
 	int in_bytes, out_bytes; // bytes per sample (1 | 2)
 	int bs, ss;             // depth - 8, effective scale shift
+	int pow16;              // 1 << (16 - ss), kept opaque so the kernels multiply (FMA pipe) instead of shifting (ALU pipe)
 	int lo[3], hi[3];       // clip range per component, already << bs
 	int uniform_pi[3];      // pattern slot when the pattern LUT selects a single slot, else -1
 	int nseg[3], tasks_per_stripe;
@@ -154,9 +155,10 @@ struct FgsParams {
 	int fblob_bytes;
 	int fpat_off[3][2];     // byte offsets inside the kernel's shared memory (after the expanded LUT)
 	int fpat_stride[3];
-	// LFSR bit-streams, one row of `wpr` words per (frame, block-row)
-	const uint32_t* streams;
-	int wpr, stream_rows, stream_row0;
+	// LFSR register per block: row (f * stream_rows + r - stream_row0) holds spitch words, word b + 1 is
+	// the register of block b of that block-row (words 0 and nb + 1 are padding for the b-1 / b+1 reads)
+	const uint32_t* states;
+	int spitch, stream_rows, stream_row0;
 };
 
 } // namespace vfgs

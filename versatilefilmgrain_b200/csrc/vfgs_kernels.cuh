@@ -1,6 +1,6 @@
 // vfgs_kernels.cuh -- the two CUDA kernels of the hot path (sm_100a).
 //
-//   lfsr_streams_kernel  replaces the serial LFSR chain of vfgs_hw.c:74-79,291-298,309-310: one warp
+//   lfsr_states_kernel   replaces the serial LFSR chain of vfgs_hw.c:74-79,291-298,309-310: one warp
 //                        per (frame, block-row) jumps the epoch state ahead by
 //                        t = (f (R-1) + r) nb steps with 32x32 GF(2) matrix powers (one output bit
 //                        per lane, gathered by a ballot) and emits the row's bit-stream, 32 bits per
@@ -52,12 +52,16 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gm
 	             :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// ---- LFSR bit-streams ----------------------------------------------------------------------
-// streams[(f * R + r) * wpr + w] = register value 32 w steps after block 0 of block-row r of frame
-// frame0 + f, i.e. bits [32w, 32w+32) of that row's stream. pow2 = JumpTable as uint32[64][32].
+// ---- LFSR registers per block -------------------------------------------------------------
+// states[(f * R + r) * spitch + 1 + b] = LFSR register of block b of block-row r of frame frame0 + f
+// (words 0 and nb + 1 of a row are padding). One warp per (frame, block-row): jump the epoch register
+// ahead by t = ((frame0 + f) (R - 1) + r) nb steps with the matrix powers pow2 (JumpTable as
+// uint32[64][32]; lane i owns output bit i, a ballot assembles the word), then walk the row 32 steps
+// at a time: consecutive blocks are consecutive 32-bit windows of one bit-stream, so lane l takes
+// window l of every {word k, word k+1} pair and the 32 registers go out as one coalesced store.
 __global__ void __launch_bounds__(kCtaThreads)
-lfsr_streams_kernel(uint32_t epoch_state, const uint32_t* __restrict__ pow2, uint32_t* __restrict__ streams,
-                    int nframes, int R, int nb, int wpr, unsigned long long frame0)
+lfsr_states_kernel(uint32_t epoch_state, const uint32_t* __restrict__ pow2, uint32_t* __restrict__ states,
+                   int nframes, int R, int nb, int spitch, unsigned long long frame0)
 {
 	const int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
 	const int lane = threadIdx.x & 31;
@@ -69,10 +73,12 @@ lfsr_streams_kernel(uint32_t epoch_state, const uint32_t* __restrict__ pow2, uin
 	for (int k = 0; t; k++, t >>= 1)
 		if (t & 1ull) s = __ballot_sync(0xffffffffu, __popc(pow2[k * 32 + lane] & s) & 1);
 	const uint32_t step32 = pow2[5 * 32 + lane];
-	uint32_t* dst = streams + (size_t)warp * wpr;
-	for (int w = 0; w < wpr; w++) {
-		if (lane == 0) dst[w] = s;
-		s = __ballot_sync(0xffffffffu, __popc(step32 & s) & 1);
+	uint32_t* dst = states + (size_t)warp * spitch;
+	if (lane == 0) { dst[0] = 0; dst[nb + 1] = 0; }
+	for (int b0 = 0; b0 < nb; b0 += 32) {
+		const uint32_t next = __ballot_sync(0xffffffffu, __popc(step32 & s) & 1);
+		if (b0 + lane < nb) dst[1 + b0 + lane] = __funnelshift_r(s, next, lane);
+		s = next;
 	}
 }
 
@@ -94,7 +100,7 @@ fgs_apply_kernel(const __grid_constant__ FgsParams p)
 	const int lane = threadIdx.x & 31;
 	const long long stride = (long long)gridDim.x * kWarpsPerCta;
 	for (long long task = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); task < p.total_tasks; task += stride)
-		process_task(p, tab, task, lane);
+		process_task(p, tab, (uint32_t)task, lane);
 }
 
 // Fast path: single-pattern components, aligned rows (fgs_fast.h). 512-thread persistent CTAs, two
@@ -110,24 +116,29 @@ fgs_apply_fast_kernel(const __grid_constant__ FgsParams p)
 	extern __shared__ __align__(128) uint8_t smem[];
 	__shared__ __align__(8) uint64_t bar;
 
+	// the replicated LUT sits on a 32 KB boundary of the shared window (the launch reserves the slack)
+	uint8_t* lut_ptr = smem + ((0u - smem_u32(smem)) & (uint32_t)(kLutAlign - 1));
+	uint8_t* img_ptr = lut_ptr + kLutBytes;
+
 	if (threadIdx.x == 0) mbar_init(&bar, 1);
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		mbar_arrive_expect_tx(&bar, (uint32_t)p.fblob_bytes);
-		bulk_copy_g2s(smem + kLutBytes, p.fblob, (uint32_t)p.fblob_bytes, &bar);
+		bulk_copy_g2s(img_ptr, p.fblob, (uint32_t)p.fblob_bytes, &bar);
 	}
 	mbar_wait(&bar, 0);
 	{
-		const uint32_t* compact = (const uint32_t*)(smem + kLutBytes);
-		uint32_t* lut = (uint32_t*)smem;
+		const uint32_t* compact = (const uint32_t*)img_ptr;
+		uint32_t* lut = (uint32_t*)lut_ptr;
 		for (int i = threadIdx.x; i < 256 * 32; i += kFastThreads) lut[i] = compact[i >> 5];
 	}
 	__syncthreads();
 
 	const int lane = threadIdx.x & 31;
+	const smem_addr_t lut = smem_addr(lut_ptr), img = smem_addr(img_ptr);
 	const long long stride = (long long)gridDim.x * kFastWarps;
 	for (long long task = (long long)blockIdx.x * kFastWarps + (threadIdx.x >> 5); task < p.total_tasks; task += stride)
-		process_task_fast<IN16, OUT8>(p, smem, task, lane);
+		process_task_fast<IN16, OUT8>(p, lut, img, (uint32_t)task, lane);
 }
 
 } // namespace vfgs

@@ -83,8 +83,8 @@ inline void build_tables(const HwState& h, TableInfo& g_bi, std::vector<uint8_t>
 				if (h.pattern[c ? 1 : 0][slot][r][x] == -128) { ok = false; break; }
 		g_bi.fast_ok[c] = ok;
 		g_bi.fpat_stride[c] = cols;
-		g_bi.fpat_off[c][0] = kLutBytes + off;
-		g_bi.fpat_off[c][1] = kLutBytes + off + rows * cols;
+		g_bi.fpat_off[c][0] = off;
+		g_bi.fpat_off[c][1] = off + rows * cols;
 		off += 2 * rows * cols;
 	}
 	g_bi.fbytes = (off + 16 + 15) & ~15; // +16: the unaligned octet fetch may touch one word past a row
@@ -94,8 +94,8 @@ inline void build_tables(const HwState& h, TableInfo& g_bi, std::vector<uint8_t>
 	for (int c = 0; c < 3; c++) {
 		if (!g_bi.fast_ok[c]) continue;
 		const int rows = c ? crows : 64, cols = c ? ccols : 64;
-		int8_t* plus = (int8_t*)&g_fblob[g_bi.fpat_off[c][0] - kLutBytes];
-		int8_t* minus = (int8_t*)&g_fblob[g_bi.fpat_off[c][1] - kLutBytes];
+		int8_t* plus = (int8_t*)&g_fblob[g_bi.fpat_off[c][0]];
+		int8_t* minus = (int8_t*)&g_fblob[g_bi.fpat_off[c][1]];
 		for (int r = 0; r < rows; r++)
 			for (int x = 0; x < cols; x++) {
 				const int8_t v = h.pattern[c ? 1 : 0][g_bi.uniform_pi[c]][r][x];
@@ -111,6 +111,7 @@ inline void fill_state_params(FgsParams& p, const HwState& h, const TableInfo& b
 {
 	p.subx = h.csubx; p.suby = h.csuby;
 	p.bs = h.bs; p.ss = h.scale_shift;
+	p.pow16 = 1 << (16 - h.scale_shift);
 	for (int c = 0; c < 3; c++) {
 		p.lo[c] = (c ? h.c_min : h.y_min) << h.bs;
 		p.hi[c] = (c ? h.c_max : h.y_max) << h.bs;

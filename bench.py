@@ -342,7 +342,9 @@ def run_b200_arm(args):
 
     peak, peak_src = measured_peak_gbs()
     algo_bytes = F * (in_bytes + out_bytes)
-    achieved = algo_bytes / (k_ms / max(k_n, 1) * 1e-3) / 1e9 if k_n else None
+    # grain kernels of one step (one launch for single-pattern configs, two when components split
+    # between the fast and the gather kernel): algorithmic bytes of the step / their summed device time
+    achieved = algo_bytes / (k_ms / args.steps * 1e-3) / 1e9 if k_n else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -354,7 +356,8 @@ def run_b200_arm(args):
         "gpu_launches": int(gpu_launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
-                     "kernel": "fgs_apply_kernel", "bytes_per_launch": algo_bytes, "avg_launch_ms": (k_ms / k_n) if k_n else None,
+                     "kernel": "+".join(hw.last_launch()["kernels"]), "launches_per_step": k_n / max(args.steps, 1),
+                     "bytes_per_launch": algo_bytes, "avg_launch_ms": (k_ms / args.steps) if k_n else None,
                      "kernel_share_of_step": (k_ms / ms) if ms else None,
                      "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None},
         "bytes_per_frame": in_bytes + out_bytes,

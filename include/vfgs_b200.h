@@ -98,13 +98,15 @@ uint64_t vfgs_b200_launch_count(void);
 int vfgs_b200_kernel_timing(int enable);
 int vfgs_b200_kernel_time(double* total_ms, uint64_t* launches);
 
-/* Test aid: route every component through the general (sample-adaptive) grain kernel even where
- * the single-pattern fast kernel would qualify. Both are CUDA paths. */
-void vfgs_b200_force_general_kernel(int on);
+/* Test aid: kernel selection. 0 = automatic (fast kernel for single-pattern components, gather kernel
+ * for sample-adaptive ones, general kernel for ragged/unaligned layouts), 1 = general kernel for
+ * everything, 2 = gather kernel wherever it can run. All three are CUDA paths. */
+void vfgs_b200_force_general_kernel(int mode);
 
 /* Geometry of the last grain kernel launch: out[0]=grid, out[1]=block, out[2]=dynamic smem bytes,
- * out[3]=SM count of the bound device. */
-void vfgs_b200_last_launch(int out[4]);
+ * out[3]=SM count of the bound device, out[4]=which grain kernels the last frame call launched
+ * (bit 0 fast, bit 1 general, bit 2 gather). */
+void vfgs_b200_last_launch(int out[5]);
 
 #ifdef __cplusplus
 }

@@ -28,15 +28,22 @@ void run_fast(const FgsParams& p, const uint8_t* lut, const uint8_t* img)
 	for (long long task = 0; task < p.total_tasks; task++)
 		for (int lane = 0; lane < 32; lane++) process_task_fast<IN16, OUT8>(p, smem_addr(lut), smem_addr(img), (uint32_t)task, lane);
 }
+
+template <bool IN16, bool OUT8>
+void run_gather(const FgsParams& p, const uint8_t* luts, const uint8_t* img)
+{
+	for (long long task = 0; task < p.total_tasks; task++)
+		for (int lane = 0; lane < 32; lane++) process_task_gather<IN16, OUT8>(p, smem_addr(luts), smem_addr(img), (uint32_t)task, lane);
+}
 } // namespace
 
 extern "C" int emu_state_size(void) { return (int)sizeof(StateDump); }
 
 // Packed planar frames, whole frames, like vfgs_b200_add_grain_frames_device.
-// force_general != 0 routes everything through the general task code. Returns a bit mask:
-// 1 = fast task code ran, 2 = general task code ran.
+// mode: 0 automatic kernel choice, 1 general task code everywhere, 2 gather task code wherever it can
+// run (plan_launches). Returns a bit mask: 1 = fast, 2 = general, 4 = gather task code ran.
 extern "C" int emu_add_grain_frames(const void* state, const void* in, void* out, int nframes, int width,
-                                    int height, int out_depth, int first_frame_index, int force_general)
+                                    int height, int out_depth, int first_frame_index, int mode)
 {
 	const StateDump& d = *(const StateDump*)state;
 	static const JumpTable jt;
@@ -99,16 +106,36 @@ extern "C" int emu_add_grain_frames(const void* state, const void* in, void* out
 	p.states = states.data(); p.spitch = spitch; p.stream_rows = R; p.stream_row0 = 0;
 	finish_tasks(p);
 
-	FgsParams pf, pg;
-	bool any_fast, any_general;
-	split_fast_general(p, bi, force_general != 0, pf, pg, any_fast, any_general);
-	if (any_fast) {
-		if (isz == 1) run_fast<false, false>(pf, lut_ptr, img_ptr);
-		else if (osz == 1) run_fast<true, true>(pf, lut_ptr, img_ptr);
-		else run_fast<true, false>(pf, lut_ptr, img_ptr);
+	LaunchPlan lp;
+	plan_launches(p, bi, mode, in == out, 227 * 1024, lp);
+	if (lp.any_fast) {
+		if (isz == 1) run_fast<false, false>(lp.fast, lut_ptr, img_ptr);
+		else if (osz == 1) run_fast<true, true>(lp.fast, lut_ptr, img_ptr);
+		else run_fast<true, false>(lp.fast, lut_ptr, img_ptr);
 	}
-	if (any_general)
-		for (long long task = 0; task < pg.total_tasks; task++)
-			for (int lane = 0; lane < 32; lane++) process_task(pg, tab, (uint32_t)task, lane);
-	return (any_fast ? 1 : 0) | (any_general ? 2 : 0);
+	if (lp.any_gather) {
+		// what fgs_apply_gather_kernel builds in shared memory: one private LUT per gather component, then the image
+		const FgsParams& g = lp.gather;
+		std::vector<uint8_t> gstore((size_t)kLutAlign + (size_t)g.ngather * kLutBytes + blob.size() + 64);
+		uint8_t* gl = (uint8_t*)(((uintptr_t)gstore.data() + kLutAlign - 1) & ~(uintptr_t)(kLutAlign - 1));
+		uint8_t* gi = gl + (size_t)g.ngather * kLutBytes;
+		memcpy(gi, blob.data(), blob.size());
+		for (int c = 0; c < 3; c++) {
+			if (g.glut_index[c] < 0) continue;
+			const uint16_t* compact = (const uint16_t*)(gi + g.lut_off) + c * 256;
+			uint32_t* lut = (uint32_t*)(gl + (size_t)g.glut_index[c] * kLutBytes);
+			const uint32_t slot_bytes = (uint32_t)g.pat_size[c ? 1 : 0];
+			for (int i = 0; i < 256 * 32; i++) {
+				const uint32_t e = compact[i >> 5];
+				lut[i] = (e & 0xffu) | (((e >> 8) * slot_bytes) << 8);
+			}
+		}
+		if (isz == 1) run_gather<false, false>(g, gl, gi);
+		else if (osz == 1) run_gather<true, true>(g, gl, gi);
+		else run_gather<true, false>(g, gl, gi);
+	}
+	if (lp.any_general)
+		for (long long task = 0; task < lp.general.total_tasks; task++)
+			for (int lane = 0; lane < 32; lane++) process_task(lp.general, tab, (uint32_t)task, lane);
+	return (lp.any_fast ? 1 : 0) | (lp.any_general ? 2 : 0) | (lp.any_gather ? 4 : 0);
 }

@@ -57,14 +57,14 @@ def test_every_golden_case(hw, case):
         frames = synth_frames(n, w, h, meta["fmt"], meta["depth"], seed=iseed)
         o = Oracle(); program_case(o, G, case)
         exp = o.add_grain_frames(frames, n, w, h, od)
-        for general_only in (False, True):  # fast kernel where it qualifies / general kernel everywhere
+        for general_only in (0, 1, 2):  # automatic kernel choice / general kernel everywhere / gather kernel wherever it can run
             hw.reset()
             program_case(hw, G, case)
             hw.force_general_kernel(general_only)
             try:
                 got = run_device(hw, frames, n, w, h, od, meta["depth"])
             finally:
-                hw.force_general_kernel(False)
+                hw.force_general_kernel(0)
             assert np.array_equal(got, exp), (case, key, general_only, first_mismatch(got, exp, w, h, meta["fmt"], n))
             assert sha(got) == want["sha256"], (case, key)
             assert hw.get_lfsr() == want["lfsr_after"], (case, key)

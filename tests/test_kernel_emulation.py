@@ -21,13 +21,14 @@ def emu():
     return L
 
 
-def run_emu(emu, o: Oracle, frames, n, w, h, od, first=0, force_general=False):
-    """Returns (output, mask): mask bit 0 = fast task code ran, bit 1 = general task code ran."""
+def run_emu(emu, o: Oracle, frames, n, w, h, od, first=0, mode=0):
+    """mode: 0 automatic, 1 general task code only, 2 gather task code wherever possible.
+    Returns (output, mask): mask bit 0 = fast, bit 1 = general, bit 2 = gather task code ran."""
     st = RefState()
     o.L.oracle_get_state(o.h, C.byref(st))
     depth = 8 + st.bs
     out = np.zeros(frames.shape, dtype=np.uint8 if (od == 8 or depth == 8) else np.uint16)
-    mask = emu.emu_add_grain_frames(C.byref(st), _ptr(frames), _ptr(out), n, w, h, od, first, 1 if force_general else 0)
+    mask = emu.emu_add_grain_frames(C.byref(st), _ptr(frames), _ptr(out), n, w, h, od, first, mode)
     return out, mask
 
 
@@ -38,11 +39,12 @@ def test_emulated_kernel_equals_oracle(emu, case):
         for od in ((0, 8) if meta["depth"] == 10 else (0,)):
             o = Oracle(); program_case(o, G, case)
             frames = synth_frames(n, w, h, meta["fmt"], meta["depth"], seed=w + od)
-            runs = [(fg, run_emu(emu, o, frames, n, w, h, od, force_general=fg)) for fg in (False, True)]
+            runs = [(mode, run_emu(emu, o, frames, n, w, h, od, mode=mode)) for mode in (0, 1, 2)]
             want = o.add_grain_frames(frames, n, w, h, od)  # advances o's registers: emulate first
-            for force_general, (got, mask) in runs:
-                assert np.array_equal(got, want), (case, w, h, od, force_general, first_mismatch(got, want, w, h, meta["fmt"], n))
-                assert not force_general or mask == 2
+            for mode, (got, mask) in runs:
+                assert np.array_equal(got, want), (case, w, h, od, mode, first_mismatch(got, want, w, h, meta["fmt"], n))
+                assert mode != 1 or mask == 2
+                assert mode != 2 or (mask & 1) == 0
 
 
 def test_emulated_kernel_frame_offset(emu):
@@ -69,7 +71,8 @@ def test_fast_path_is_taken_where_expected(emu):
     assert mask_of("fgs_afgs1_test1.cfg|d10|420|g100", 512, 64) == 1
     assert mask_of("fgs_sei_ff_test4.cfg|d10|444|g150", 512, 64) == 1
     assert mask_of("fgs_sei_ff_test1.cfg|d8|420|g100", 512, 64) == 1
-    assert mask_of("fgs_sei.cfg|d10|420|g100", 512, 64) == 3
+    assert mask_of("fgs_sei.cfg|d10|420|g100", 512, 64) == 5          # luma: gather, chroma: fast
+    assert mask_of("fgs_sei_ff_test5.cfg|d10|420|g100", 512, 64) == 5  # chroma: gather
     assert mask_of("fgs_afgs1_test1.cfg|d10|420|g100", 200, 64) == 3   # luma rows qualify, chroma width 100 does not
     assert mask_of("fgs_afgs1_test1.cfg|d10|420|g100", 204, 64) == 2
 
@@ -89,4 +92,4 @@ def test_fast_path_garbage_samples_and_minus_128(emu):
     o = Oracle(); program_case(o, G, case); o.vfgs_set_luma_pattern(0, np.ascontiguousarray(P))
     frames = synth_frames(n, w, h, "420", 10, seed=2)
     got, mask = run_emu(emu, o, frames, n, w, h, 0)
-    assert mask == 3 and np.array_equal(got, o.add_grain_frames(frames, n, w, h, 0))
+    assert mask == 5 and np.array_equal(got, o.add_grain_frames(frames, n, w, h, 0))

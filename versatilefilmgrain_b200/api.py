@@ -144,12 +144,13 @@ class VfgsHw:
         self._chk(self.L.vfgs_b200_kernel_time(C.byref(ms), C.byref(n)))
         return ms.value, int(n.value)
 
-    def force_general_kernel(self, on: bool): self.L.vfgs_b200_force_general_kernel(1 if on else 0)
+    def force_general_kernel(self, mode): self.L.vfgs_b200_force_general_kernel(int(mode))
 
     def last_launch(self) -> dict:
-        a = (C.c_int * 4)()
+        a = (C.c_int * 5)()
         self.L.vfgs_b200_last_launch(a)
-        return {"grid": a[0], "block": a[1], "smem": a[2], "sms": a[3]}
+        kernels = [n for bit, n in ((1, "fgs_apply_fast_kernel"), (4, "fgs_apply_gather_kernel"), (2, "fgs_apply_kernel")) if a[4] & bit]
+        return {"grid": a[0], "block": a[1], "smem": a[2], "sms": a[3], "kernels": kernels}
 
     def state(self) -> dict:
         """Mirrored hw state as arrays (same keys as the oracle's/reference's state dumps)."""

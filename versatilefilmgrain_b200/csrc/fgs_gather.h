@@ -1,0 +1,272 @@
+// fgs_gather.h -- grain kernel task code for components whose pattern LUT selects SEVERAL pattern
+// slots (sample-adaptive pattern selection: the reference's built-in default SEI with 8 luma
+// patterns, cfg/fgs_sei_ff_test5-7 chroma). Same decomposition and the same memory pipeline as the
+// single-pattern path (fgs_fast.h: lane = 8 samples, 4 lines in flight with rotating refill, packed
+// 16-bit clip), but the grain byte of every sample is a true gather:
+//     entry = lut[intensity]            one conflict-free 32-bit shared load; the component has its own
+//                                       per-lane replicated table, entry = scale | slot byte offset << 8
+//     grain = pattern[slot offset + window row + column]      one byte load, bank conflicts as they fall
+// The block's random sign is applied to the fetched byte (FMA pipe), so no negated pattern copies are
+// needed and any int8 pattern value is allowed. The neighbour sample an edge filter needs is
+// recomputed from the neighbouring block's register and THAT sample's intensity (one extra 16-bit
+// global load per line and side, L1 hit), which is why this path cannot run in place.
+// Restates vfgs_hw.c:140-284 per sample like fgs_task.h; host-compilable for tests/emu.
+#pragma once
+#include "fgs_fast.h"
+
+namespace vfgs {
+
+// Shared memory: [0, 32 KB * ngather) private LUTs of the gather components (each on a 32 KB
+// boundary), then the general table image's pattern slots (gpat_off, relative to the image copy).
+struct GatherLane {
+	smem_addr_t own;        // bank + window row 0 + ox + i0 of the current block (slot offset added per sample)
+	smem_addr_t lh, rh;     // neighbour windows: last column of block b-1 / first column of block b+1
+	smem_addr_t lut;        // this lane's column of the component's private LUT
+	int stride;
+	bool has_left, has_right;
+	int s_own, s_l, s_r;    // block signs
+	int pow16;
+	uint32_t lo2, hi2;
+};
+struct GatherUp {
+	smem_addr_t own, lh, rh;
+	int s_own, s_l, s_r;
+};
+
+VFGS_HD void ld_cached_16(const uint8_t* p, uint32_t r[4])
+{
+#if defined(__CUDA_ARCH__)
+	asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "l"(p));
+#else
+	memcpy(r, p, 16);
+#endif
+}
+VFGS_HD void ld_cached_8(const uint8_t* p, uint32_t r[2])
+{
+#if defined(__CUDA_ARCH__)
+	asm volatile("ld.global.v2.u32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "l"(p));
+#else
+	memcpy(r, p, 8);
+#endif
+}
+VFGS_HD void ld_cached_16_if(const uint8_t* p, uint32_t r[4], bool pred)
+{
+#if defined(__CUDA_ARCH__)
+	asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q ld.global.v4.u32 {%0,%1,%2,%3}, [%4];\n\t}"
+	             : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]) : "l"(p), "r"((uint32_t)pred));
+#else
+	if (pred) memcpy(r, p, 16);
+#endif
+}
+VFGS_HD void ld_cached_8_if(const uint8_t* p, uint32_t r[2], bool pred)
+{
+#if defined(__CUDA_ARCH__)
+	asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q ld.global.v2.u32 {%0,%1}, [%2];\n\t}"
+	             : "+r"(r[0]), "+r"(r[1]) : "l"(p), "r"((uint32_t)pred));
+#else
+	if (pred) memcpy(r, p, 8);
+#endif
+}
+// one sample (IB bytes wide) when pred is set, else 0
+template <int IB>
+VFGS_HD uint32_t ld_sample_if(const uint8_t* p, bool pred)
+{
+	if (!pred) return 0;
+	return IB == 2 ? (uint32_t)*(const uint16_t*)p : (uint32_t)*p;
+}
+
+// LUT index bits (intensity * 128) of sample e of a lane's raw words.
+template <bool IN16, int E>
+VFGS_HD uint32_t index_bits(const uint32_t raw[4])
+{
+	if (IN16) {
+		const uint32_t w = raw[E >> 1];
+		return (E & 1) ? (mulhi_u32(w, 1u << 21) & 0x7f80u) : ((w << 5) & 0x7f80u); // ((v >> 2) & 0xff) << 7
+	} else {
+		const uint32_t w = raw[E >> 2];
+		constexpr int sh = (E & 3) * 8;
+		return sh >= 7 ? (w >> (sh - 7)) & 0x7f80u : (w << (7 - sh)) & 0x7f80u;      // v << 7
+	}
+}
+
+// entry -> scale and signed grain of one sample (column E of the lane's window)
+template <int E>
+VFGS_HD void gather_sample(const GatherLane& L, const GatherUp& U, uint32_t ibits, int rc, int wc_s, int wu_s, int ru,
+                           int& scale, int& grain)
+{
+	const uint32_t ent = lds32(L.lut | (smem_addr_t)ibits);
+	scale = (int)(ent & 0xff);
+	const smem_addr_t off = (smem_addr_t)(ent >> 8) + E;
+	int g = lds_s8(L.own + rc + off);
+	if (wu_s == 0 && wc_s == 0) g *= L.s_own;
+	else g = (g * wc_s + lds_s8(U.own + ru + off) * wu_s + 16) >> 5; // weights carry the two block signs
+	grain = g;
+}
+
+template <bool IN16, bool OUT8>
+VFGS_HD void gather_line(const GatherLane& L, const GatherUp& U, int rc, int w_cur, int w_up, int ru, int in_shift,
+                         const uint32_t raw[4], uint32_t vl, uint32_t vr, uint32_t outw[4])
+{
+	const int wc_s = w_cur * L.s_own, wu_s = w_up * U.s_own;
+	int g[8], sc[8];
+	gather_sample<0>(L, U, index_bits<IN16, 0>(raw), rc, wc_s, wu_s, ru, sc[0], g[0]);
+	gather_sample<1>(L, U, index_bits<IN16, 1>(raw), rc, wc_s, wu_s, ru, sc[1], g[1]);
+	gather_sample<2>(L, U, index_bits<IN16, 2>(raw), rc, wc_s, wu_s, ru, sc[2], g[2]);
+	gather_sample<3>(L, U, index_bits<IN16, 3>(raw), rc, wc_s, wu_s, ru, sc[3], g[3]);
+	gather_sample<4>(L, U, index_bits<IN16, 4>(raw), rc, wc_s, wu_s, ru, sc[4], g[4]);
+	gather_sample<5>(L, U, index_bits<IN16, 5>(raw), rc, wc_s, wu_s, ru, sc[5], g[5]);
+	gather_sample<6>(L, U, index_bits<IN16, 6>(raw), rc, wc_s, wu_s, ru, sc[6], g[6]);
+	gather_sample<7>(L, U, index_bits<IN16, 7>(raw), rc, wc_s, wu_s, ru, sc[7], g[7]);
+
+	// neighbours' edge samples (their own intensity selects their pattern slot), then the edge filter
+	if (L.has_left) {
+		const smem_addr_t off = (smem_addr_t)(lds32(L.lut | (smem_addr_t)(((vl >> in_shift) & 0xffu) << 7)) >> 8);
+		int h = lds_s8(L.lh + rc + off);
+		if (w_cur) h = (h * (w_cur * L.s_l) + lds_s8(U.lh + ru + off) * (w_up * U.s_l) + 16) >> 5;
+		else h *= L.s_l;
+		g[0] = (h + 3 * g[0] + g[1] + 2) >> 2;
+	}
+	// (g[0] above reads g[1] unfiltered; g[7] below reads g[6] unfiltered: a lane has 8 samples)
+	if (L.has_right) {
+		const smem_addr_t off = (smem_addr_t)(lds32(L.lut | (smem_addr_t)(((vr >> in_shift) & 0xffu) << 7)) >> 8);
+		int h = lds_s8(L.rh + rc + off);
+		if (w_cur) h = (h * (w_cur * L.s_r) + lds_s8(U.rh + ru + off) * (w_up * U.s_r) + 16) >> 5;
+		else h *= L.s_r;
+		g[7] = (g[6] + 3 * g[7] + h + 2) >> 2;
+	}
+
+	if (IN16) {
+		uint32_t r[4];
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			const int a_lo = sc[2 * k] * (g[2 * k] * L.pow16) + 0x8000;
+			const int a_hi = sc[2 * k + 1] * (g[2 * k + 1] * L.pow16) + 0x8000;
+			const uint32_t d2 = prmt((uint32_t)a_lo, (uint32_t)a_hi, 0x7632);
+			const uint32_t v2 = min_u16x2(raw[k], 0x3fff3fffu);
+			r[k] = min_s16x2(add_max_s16x2(v2, d2, L.lo2), L.hi2);
+		}
+		if (OUT8) {
+#pragma unroll
+			for (int k = 0; k < 4; k++) r[k] = ((r[k] + 0x00020002u) >> 2) & 0x00ff00ffu;
+			outw[0] = prmt(r[0], r[1], 0x6420);
+			outw[1] = prmt(r[2], r[3], 0x6420);
+		} else {
+			outw[0] = r[0]; outw[1] = r[1]; outw[2] = r[2]; outw[3] = r[3];
+		}
+	} else {
+		const int lo = (int)(L.lo2 & 0xffff), hi = (int)(L.hi2 & 0xffff);
+		int o[8];
+#pragma unroll
+		for (int e = 0; e < 8; e++) {
+			const int v = (int)((raw[e >> 2] >> ((e & 3) * 8)) & 0xff);
+			int x = v + ((sc[e] * (g[e] * L.pow16) + 0x8000) >> 16);
+			x = x > hi ? hi : x;
+			o[e] = x < lo ? lo : x;
+		}
+		outw[0] = (uint32_t)o[0] | ((uint32_t)o[1] << 8) | ((uint32_t)o[2] << 16) | ((uint32_t)o[3] << 24);
+		outw[1] = (uint32_t)o[4] | ((uint32_t)o[5] << 8) | ((uint32_t)o[6] << 16) | ((uint32_t)o[7] << 24);
+	}
+}
+
+// Window address (without slot offset) and sign of a block.
+VFGS_HD smem_addr_t gather_window(const FgsParams& p, smem_addr_t img, int c, uint32_t state, int col, int& sign)
+{
+	const BlockOfs o = decode_offsets(c, state, p.subx, p.suby);
+	sign = o.sign;
+	const int bank = c ? 1 : 0;
+	return img + (smem_addr_t)(p.gpat_off[bank] + o.oy * p.pat_stride[bank] + o.ox + col);
+}
+
+template <bool IN16, bool OUT8>
+VFGS_HD void process_task_gather(const FgsParams& p, smem_addr_t luts, smem_addr_t img, uint32_t task, int lane)
+{
+	const TaskGeom t = decode_task(p, task);
+	const int c = t.c;
+	const Plane& pl = p.comp[c];
+	const int ysh = (c && p.suby > 1) ? 1 : 0;
+	const int nsh = (c && p.subx > 1) ? 3 : 4;
+	const int n = 1 << nsh;
+	const int k0 = t.seg * kSegSamples + lane * kSamplesPerLane;
+	if (k0 >= pl.width) return;
+
+	const int cl0 = (t.r * 16) >> ysh;
+	int cl1 = cl0 + (16 >> ysh);
+	if (cl1 > pl.lines) cl1 = pl.lines;
+	const int nl = cl1 - cl0;
+	if (nl <= 0) return;
+
+	constexpr int IB = IN16 ? 2 : 1, OB = (IN16 && !OUT8) ? 2 : 1;
+	const long long in_pitch = pl.in_row_bytes, out_pitch = pl.out_row_bytes;
+	const uint8_t* src = pl.in + (long long)t.f * p.in_frame_bytes + (long long)cl0 * in_pitch + (long long)k0 * IB;
+	uint8_t* dst = pl.out + (long long)t.f * p.out_frame_bytes + (long long)cl0 * out_pitch + (long long)k0 * OB;
+
+	const int b = k0 >> nsh;
+	const int i0 = k0 & (n - 1);
+	GatherLane L;
+	L.has_left = (i0 == 0) && (b > 0);
+	L.has_right = (i0 + kSamplesPerLane == n) && (b + 1 < p.nb);
+	const bool right_in_picture = k0 + kSamplesPerLane < pl.width; // samples right of the picture read as 0
+
+	uint32_t raw[kFastLB][4], vl[kFastLB], vr[kFastLB];
+#pragma unroll
+	for (int q = 0; q < kFastLB; q++) {
+		const uint8_t* row = src + (q < nl ? q : nl - 1) * in_pitch;
+		if (IN16) ld_cached_16(row, raw[q]);
+		else ld_cached_8(row, raw[q]);
+		vl[q] = ld_sample_if<IB>(row - IB, L.has_left);
+		vr[q] = ld_sample_if<IB>(row + kSamplesPerLane * IB, L.has_right && right_in_picture);
+	}
+
+	const int bank = c ? 1 : 0;
+	L.stride = p.pat_stride[bank];
+	L.lut = luts + (smem_addr_t)(p.glut_index[c] * kLutBytes + lane * 4);
+	L.pow16 = p.pow16;
+	L.lo2 = (uint32_t)p.lo[c] * 0x00010001u; L.hi2 = (uint32_t)p.hi[c] * 0x00010001u;
+
+	const int srow = t.r - p.stream_row0;
+	const uint32_t* row_cur = p.states + ((long long)t.f * p.stream_rows + srow) * p.spitch + 1 + b;
+	L.own = gather_window(p, img, c, row_cur[0], i0, L.s_own);
+	L.lh = L.rh = L.own; L.s_l = L.s_r = 1;
+	if (L.has_left) L.lh = gather_window(p, img, c, row_cur[-1], n - 1, L.s_l);
+	if (L.has_right) L.rh = gather_window(p, img, c, row_cur[1], 0, L.s_r);
+
+	GatherUp U;
+	U.own = U.lh = U.rh = L.own; U.s_own = U.s_l = U.s_r = 1;
+	bool ovl = t.r > 0;
+	if (ovl) {
+		const uint32_t* row_up = row_cur - p.spitch;
+		U.own = gather_window(p, img, c, row_up[0], i0, U.s_own);
+		if (L.has_left) U.lh = gather_window(p, img, c, row_up[-1], n - 1, U.s_l);
+		if (L.has_right) U.rh = gather_window(p, img, c, row_up[1], 0, U.s_r);
+	}
+
+	int rc = 0;
+	const uint8_t* nxt = src + kFastLB * in_pitch;
+#pragma unroll 1
+	for (int base = 0; base < nl; base += kFastLB) {
+#pragma unroll
+		for (int q = 0; q < kFastLB; q++) {
+			const int line = base + q;
+			uint32_t w[4];
+			int w_cur = 0, w_up = 0, ru = 0;
+			if (q == 0 && ovl) { w_cur = ysh ? 20 : 12; w_up = ysh ? 20 : 24; ru = (16 >> ysh) * L.stride; }
+			if (q == 1 && ovl && !ysh) { w_cur = 24; w_up = 12; ru = 17 * L.stride; }
+			gather_line<IN16, OUT8>(L, U, rc, w_cur, w_up, ru, p.bs, raw[q], vl[q], vr[q], w);
+			const bool more = line + kFastLB < nl;
+			if (IN16) ld_cached_16_if(nxt, raw[q], more);
+			else ld_cached_8_if(nxt, raw[q], more);
+			if (more) {
+				vl[q] = ld_sample_if<IB>(nxt - IB, L.has_left);
+				vr[q] = ld_sample_if<IB>(nxt + kSamplesPerLane * IB, L.has_right && right_in_picture);
+			}
+			if (line < nl) {
+				if (OB == 2) st_global_16(dst, w);
+				else st_global_8(dst, w);
+			}
+			rc += L.stride; nxt += in_pitch; dst += out_pitch;
+		}
+		ovl = false;
+	}
+}
+
+} // namespace vfgs

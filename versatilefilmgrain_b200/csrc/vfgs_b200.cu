@@ -39,7 +39,7 @@ struct Context {
 	size_t blob_cap = 0;
 	uint8_t* d_fblob = nullptr; // fast-path table image
 	size_t fblob_cap = 0;
-	int fast_smem_attr = 0;
+	int fast_smem_attr = 0, gather_smem_attr = 0;
 	uint32_t* d_streams = nullptr; // device entry point / line path
 	size_t streams_cap = 0;
 	cudaStream_t last_stream = nullptr;
@@ -49,7 +49,7 @@ struct Context {
 	uint8_t* d_line = nullptr; // compat line path staging
 	size_t line_cap = 0;
 	int smem_attr = 0;
-	int last_launch[4] = {0, 0, 0, 0};
+	int last_launch[5] = {0, 0, 0, 0, 0};
 	// optional per-launch timing of the grain kernel (vfgs_b200_kernel_timing)
 	bool timing = false;
 	std::vector<cudaEvent_t> ev_begin, ev_end;
@@ -66,7 +66,7 @@ std::vector<uint8_t> g_blob;
 TableInfo g_bi;
 std::vector<uint8_t> g_fblob;
 uint64_t g_launches = 0;
-bool g_force_general = false; // test hook: route every component through the general kernel
+int g_kernel_mode = 0; // test hook: 0 auto, 1 general kernel everywhere, 2 gather kernel wherever it can run
 char g_err[512] = "";
 const JumpTable& jump_table()
 {
@@ -220,18 +220,29 @@ void fill_common(FgsParams& p, const Geometry& g)
 }
 
 typedef void (*GrainKernel)(const FgsParams);
+enum KernelKind { kGeneral = 0, kFast = 1, kGather = 2 };
 
-int launch_apply(const FgsParams& p, cudaStream_t stream, bool fast = false)
+int launch_apply(const FgsParams& p, cudaStream_t stream, KernelKind kind = kGeneral, int gather_smem = 0)
 {
 	Context& c = g_ctx;
 	if (p.total_tasks <= 0) return VFGS_B200_OK;
 	if (p.total_tasks >= (1ll << 31)) return set_err(VFGS_B200_ERR_ARG, "batch too large for one launch (%lld warp-tasks): split the call", p.total_tasks);
 	GrainKernel kern = fgs_apply_kernel;
 	int threads = kCtaThreads, smem = p.blob_bytes;
-	if (fast) {
+	if (kind == kFast) {
 		kern = p.in_bytes == 1 ? fgs_apply_fast_kernel<false, false>
 		     : p.out_bytes == 1 ? fgs_apply_fast_kernel<true, true> : fgs_apply_fast_kernel<true, false>;
 		threads = kFastThreads; smem = kLutAlign + kLutBytes + p.fblob_bytes; // slack to place the LUT on a 32 KB boundary
+	} else if (kind == kGather) {
+		kern = p.in_bytes == 1 ? fgs_apply_gather_kernel<false, false>
+		     : p.out_bytes == 1 ? fgs_apply_gather_kernel<true, true> : fgs_apply_gather_kernel<true, false>;
+		threads = kFastThreads; smem = gather_smem;
+		if (smem > c.gather_smem_attr) {
+			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_gather_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_gather_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_gather_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+			c.gather_smem_attr = smem;
+		}
 	}
 	const int wpc = threads / 32;
 	int per_sm = 0;
@@ -256,6 +267,7 @@ int launch_apply(const FgsParams& p, cudaStream_t stream, bool fast = false)
 	if (c.timing) CUDA_TRY(cudaEventRecord(e1, stream));
 	g_launches++;
 	c.last_launch[0] = grid; c.last_launch[1] = threads; c.last_launch[2] = smem; c.last_launch[3] = c.sm_count;
+	c.last_launch[4] |= kind == kFast ? 1 : kind == kGather ? 4 : 2;
 	return VFGS_B200_OK;
 }
 
@@ -307,14 +319,16 @@ int run_frames_device(const vfgs_b200_planes& in, const vfgs_b200_planes& out, i
 	p.states = d_streams; p.stream_rows = g.R; p.stream_row0 = 0;
 	finish_tasks(p);
 	if (int rc = launch_streams(epoch, d_streams, n, g, frame0, stream)) return rc;
-	// components that qualify go through the fast kernel, the rest through the general one
-	FgsParams pf, pg;
-	bool any_fast, any_general;
-	split_fast_general(p, g_bi, g_force_general, pf, pg, any_fast, any_general);
-	if (any_fast)
-		if (int rc = launch_apply(pf, stream, true)) return rc;
-	if (any_general)
-		if (int rc = launch_apply(pg, stream, false)) return rc;
+	// every component goes to the cheapest kernel that can serve it (plan_launches)
+	g_ctx.last_launch[4] = 0;
+	LaunchPlan lp;
+	plan_launches(p, g_bi, g_kernel_mode, in.y == out.y, g_ctx.max_smem_optin - 1024, lp);
+	if (lp.any_fast)
+		if (int rc = launch_apply(lp.fast, stream, kFast)) return rc;
+	if (lp.any_gather)
+		if (int rc = launch_apply(lp.gather, stream, kGather, lp.gather_smem)) return rc;
+	if (lp.any_general)
+		if (int rc = launch_apply(lp.general, stream, kGeneral)) return rc;
 	return VFGS_B200_OK;
 }
 
@@ -633,7 +647,7 @@ void vfgs_b200_host_free(void* p)
 
 uint64_t vfgs_b200_launch_count(void) { return g_launches; }
 
-void vfgs_b200_force_general_kernel(int on) { g_force_general = on != 0; }
+void vfgs_b200_force_general_kernel(int mode) { g_kernel_mode = mode; }
 
 int vfgs_b200_kernel_timing(int enable)
 {
@@ -660,9 +674,9 @@ int vfgs_b200_kernel_time(double* total_ms, uint64_t* launches)
 	return VFGS_B200_OK;
 }
 
-void vfgs_b200_last_launch(int out[4])
+void vfgs_b200_last_launch(int out[5])
 {
-	for (int i = 0; i < 4; i++) out[i] = g_ctx.last_launch[i];
+	for (int i = 0; i < 5; i++) out[i] = g_ctx.last_launch[i];
 }
 
 } // extern "C"

@@ -155,6 +155,10 @@ struct FgsParams {
 	int fblob_bytes;
 	int fpat_off[3][2];     // byte offsets inside the kernel's shared memory (after the expanded LUT)
 	int fpat_stride[3];
+	// gather path (fgs_gather.h): private LUT slot of each component (-1: none) and the pattern banks'
+	// offsets inside the general image
+	int glut_index[3], ngather;
+	int gpat_off[2];
 	// LFSR register per block: row (f * stream_rows + r - stream_row0) holds spitch words, word b + 1 is
 	// the register of block b of that block-row (words 0 and nb + 1 are padding for the b-1 / b+1 reads)
 	const uint32_t* states;

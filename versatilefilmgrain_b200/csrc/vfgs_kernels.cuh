@@ -12,7 +12,7 @@
 //                        loads and stores.
 #pragma once
 #include <cuda_runtime.h>
-#include "fgs_fast.h"
+#include "fgs_gather.h"
 
 namespace vfgs {
 
@@ -139,6 +139,45 @@ fgs_apply_fast_kernel(const __grid_constant__ FgsParams p)
 	const long long stride = (long long)gridDim.x * kFastWarps;
 	for (long long task = (long long)blockIdx.x * kFastWarps + (threadIdx.x >> 5); task < p.total_tasks; task += stride)
 		process_task_fast<IN16, OUT8>(p, lut, img, (uint32_t)task, lane);
+}
+
+// Gather path: components with sample-adaptive pattern selection (fgs_gather.h). Shared memory: one
+// per-lane replicated LUT (32 KB, entry = scale | slot byte offset << 8) per gather component, each on a
+// 32 KB boundary, then the general table image (compact LUTs + pattern slots) brought in by one bulk copy.
+template <bool IN16, bool OUT8>
+__global__ void __launch_bounds__(kFastThreads, 2)
+fgs_apply_gather_kernel(const __grid_constant__ FgsParams p)
+{
+	extern __shared__ __align__(128) uint8_t smem[];
+	__shared__ __align__(8) uint64_t bar;
+
+	uint8_t* lut_ptr = smem + ((0u - smem_u32(smem)) & (uint32_t)(kLutAlign - 1));
+	uint8_t* img_ptr = lut_ptr + p.ngather * kLutBytes;
+
+	if (threadIdx.x == 0) mbar_init(&bar, 1);
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		mbar_arrive_expect_tx(&bar, (uint32_t)p.blob_bytes);
+		bulk_copy_g2s(img_ptr, p.blob, (uint32_t)p.blob_bytes, &bar);
+	}
+	mbar_wait(&bar, 0);
+	for (int c = 0; c < 3; c++) {
+		if (p.glut_index[c] < 0) continue;
+		const uint16_t* compact = (const uint16_t*)(img_ptr + p.lut_off) + c * 256; // scale | slot << 8
+		uint32_t* lut = (uint32_t*)(lut_ptr + p.glut_index[c] * kLutBytes);
+		const uint32_t slot_bytes = (uint32_t)p.pat_size[c ? 1 : 0];
+		for (int i = threadIdx.x; i < 256 * 32; i += kFastThreads) {
+			const uint32_t e = compact[i >> 5];
+			lut[i] = (e & 0xffu) | (((e >> 8) * slot_bytes) << 8);
+		}
+	}
+	__syncthreads();
+
+	const int lane = threadIdx.x & 31;
+	const smem_addr_t luts = smem_addr(lut_ptr), img = smem_addr(img_ptr);
+	const long long stride = (long long)gridDim.x * kFastWarps;
+	for (long long task = (long long)blockIdx.x * kFastWarps + (threadIdx.x >> 5); task < p.total_tasks; task += stride)
+		process_task_gather<IN16, OUT8>(p, luts, img, (uint32_t)task, lane);
 }
 
 } // namespace vfgs

@@ -6,7 +6,7 @@
 #include <string.h>
 #include <vector>
 
-#include "fgs_fast.h"
+#include "fgs_gather.h"
 
 namespace vfgs {
 
@@ -141,19 +141,48 @@ inline void finish_tasks(FgsParams& p)
 	p.total_tasks = (long long)p.nframes * p.rows * p.tasks_per_stripe;
 }
 
-// Split a whole-frame launch between the fast kernel (components with one pattern slot, vector-
-// aligned rows, width % 8 == 0) and the general kernel. Returns {any_fast, any_general}.
-inline void split_fast_general(const FgsParams& p, const TableInfo& bi, bool force_general, FgsParams& pf, FgsParams& pg,
-                               bool& any_fast, bool& any_general)
+// Which grain kernel serves which component of a whole-frame launch:
+//   fast    one pattern slot (no -128 byte), vector-aligned rows, width % 8 == 0        (fgs_fast.h)
+//   gather  several pattern slots (or a -128 byte), same alignment conditions, out of place (fgs_gather.h)
+//   general everything else: ragged widths, unaligned rows                               (fgs_task.h)
+// mode: 0 = as above, 1 = general kernel for everything, 2 = gather kernel wherever it can run
+// (1 and 2 exist for the tests). smem_limit: opt-in shared memory per block of the device.
+struct LaunchPlan {
+	FgsParams fast, gather, general;
+	bool any_fast, any_gather, any_general;
+	int gather_smem; // dynamic shared memory of the gather launch
+};
+
+inline void plan_launches(const FgsParams& p, const TableInfo& bi, int mode, bool in_place, int smem_limit, LaunchPlan& lp)
 {
-	pf = p; pg = p;
-	any_fast = any_general = false;
+	lp.fast = lp.gather = lp.general = p;
+	lp.any_fast = lp.any_gather = lp.any_general = false;
+	int kind[3], ngather = 0;
 	for (int c = 0; c < 3; c++) {
-		const bool fast = bi.fast_ok[c] && p.comp[c].vec && (p.comp[c].width % kSamplesPerLane) == 0 && !force_general;
-		(fast ? pg : pf).nseg[c] = 0;
-		(fast ? any_fast : any_general) = true;
+		const bool aligned = p.comp[c].vec && (p.comp[c].width % kSamplesPerLane) == 0;
+		kind[c] = 2;
+		if (aligned && mode != 1) {
+			if (bi.fast_ok[c] && mode != 2) kind[c] = 0;
+			else if (!in_place) kind[c] = 1;
+		}
+		if (kind[c] == 1) ngather++;
 	}
-	for (FgsParams* q : {&pf, &pg}) {
+	lp.gather_smem = kLutAlign + ngather * kLutBytes + bi.bytes;
+	if (ngather && lp.gather_smem > smem_limit) { // tables do not fit: those components take the general kernel
+		for (int c = 0; c < 3; c++) if (kind[c] == 1) kind[c] = 2;
+		ngather = 0;
+	}
+	int gi = 0;
+	for (int c = 0; c < 3; c++) {
+		lp.gather.glut_index[c] = kind[c] == 1 ? gi++ : -1;
+		if (kind[c] != 0) lp.fast.nseg[c] = 0;
+		if (kind[c] != 1) lp.gather.nseg[c] = 0;
+		if (kind[c] != 2) lp.general.nseg[c] = 0;
+		(kind[c] == 0 ? lp.any_fast : kind[c] == 1 ? lp.any_gather : lp.any_general) = true;
+	}
+	lp.gather.ngather = ngather;
+	lp.gather.gpat_off[0] = bi.pat_off[0]; lp.gather.gpat_off[1] = bi.pat_off[1];
+	for (FgsParams* q : {&lp.fast, &lp.gather, &lp.general}) {
 		q->tasks_per_stripe = q->nseg[0] + q->nseg[1] + q->nseg[2];
 		q->total_tasks = (long long)q->nframes * q->rows * q->tasks_per_stripe;
 	}

@@ -8,8 +8,9 @@
 //     grain = pattern[slot offset + window row + column]      one byte load, bank conflicts as they fall
 // The block's random sign is applied to the fetched byte (FMA pipe), so no negated pattern copies are
 // needed and any int8 pattern value is allowed. The neighbour sample an edge filter needs is
-// recomputed from the neighbouring block's register and THAT sample's intensity (one extra 16-bit
-// global load per line and side, L1 hit), which is why this path cannot run in place.
+// recomputed from the neighbouring block's register and THAT sample's intensity, which sits in the
+// adjacent lane's registers: one warp shuffle per side and line (only lanes 0 and 31 read their
+// neighbour sample from global memory, which is why this path cannot run in place).
 // Restates vfgs_hw.c:140-284 per sample like fgs_task.h; host-compilable for tests/emu.
 #pragma once
 #include "fgs_fast.h"
@@ -73,6 +74,32 @@ VFGS_HD uint32_t ld_sample_if(const uint8_t* p, bool pred)
 {
 	if (!pred) return 0;
 	return IB == 2 ? (uint32_t)*(const uint16_t*)p : (uint32_t)*p;
+}
+
+#if defined(__CUDA_ARCH__)
+constexpr bool kHaloFromMemory = false;
+#else
+constexpr bool kHaloFromMemory = true; // host build (tests/emu) runs lane by lane: no shuffles
+#endif
+
+// Edge samples of the two neighbouring lanes for this line. Device: the left neighbour's last and the
+// right neighbour's first sample come out of their registers by shuffle; lane 0 / lane 31 use the value
+// they loaded from memory (gl / gr). Samples right of the picture read as 0.
+template <bool IN16>
+VFGS_HD void neighbour_samples(const uint32_t raw[4], int lane, uint32_t gl, uint32_t gr, bool right_in_picture,
+                               uint32_t& vl, uint32_t& vr)
+{
+#if defined(__CUDA_ARCH__)
+	const uint32_t first = IN16 ? raw[0] & 0xffffu : raw[0] & 0xffu;
+	const uint32_t last = IN16 ? raw[3] >> 16 : raw[1] >> 24;
+	const uint32_t up = __shfl_up_sync(0xffffffffu, last, 1);
+	const uint32_t down = __shfl_down_sync(0xffffffffu, first, 1);
+	vl = lane == 0 ? gl : up;
+	vr = !right_in_picture ? 0u : lane == 31 ? gr : down;
+#else
+	(void)raw; (void)lane; (void)right_in_picture;
+	vl = gl; vr = gr;
+#endif
 }
 
 // LUT index bits (intensity * 128) of sample e of a lane's raw words.
@@ -187,34 +214,41 @@ VFGS_HD void process_task_gather(const FgsParams& p, smem_addr_t luts, smem_addr
 	const int nsh = (c && p.subx > 1) ? 3 : 4;
 	const int n = 1 << nsh;
 	const int k0 = t.seg * kSegSamples + lane * kSamplesPerLane;
-	if (k0 >= pl.width) return;
+	// lanes right of the picture stay in the loop (the neighbour exchange is a warp shuffle) but
+	// neither load nor store
+	const bool active = k0 < pl.width;
 
 	const int cl0 = (t.r * 16) >> ysh;
 	int cl1 = cl0 + (16 >> ysh);
 	if (cl1 > pl.lines) cl1 = pl.lines;
 	const int nl = cl1 - cl0;
-	if (nl <= 0) return;
+	if (nl <= 0) return; // warp-uniform
 
 	constexpr int IB = IN16 ? 2 : 1, OB = (IN16 && !OUT8) ? 2 : 1;
 	const long long in_pitch = pl.in_row_bytes, out_pitch = pl.out_row_bytes;
 	const uint8_t* src = pl.in + (long long)t.f * p.in_frame_bytes + (long long)cl0 * in_pitch + (long long)k0 * IB;
 	uint8_t* dst = pl.out + (long long)t.f * p.out_frame_bytes + (long long)cl0 * out_pitch + (long long)k0 * OB;
 
-	const int b = k0 >> nsh;
+	const int b = active ? (k0 >> nsh) : 0; // idle lanes must not index past the register row
 	const int i0 = k0 & (n - 1);
 	GatherLane L;
-	L.has_left = (i0 == 0) && (b > 0);
-	L.has_right = (i0 + kSamplesPerLane == n) && (b + 1 < p.nb);
+	L.has_left = active && (i0 == 0) && (b > 0);
+	L.has_right = active && (i0 + kSamplesPerLane == n) && (b + 1 < p.nb);
 	const bool right_in_picture = k0 + kSamplesPerLane < pl.width; // samples right of the picture read as 0
+	// who fetches a neighbour sample from memory: every lane in the host build, the warp's end lanes on the device
+	const bool mem_left = L.has_left && (kHaloFromMemory || lane == 0);
+	const bool mem_right = L.has_right && right_in_picture && (kHaloFromMemory || lane == 31);
 
-	uint32_t raw[kFastLB][4], vl[kFastLB], vr[kFastLB];
+	uint32_t raw[kFastLB][4] = {}, vl[kFastLB], vr[kFastLB];
 #pragma unroll
 	for (int q = 0; q < kFastLB; q++) {
 		const uint8_t* row = src + (q < nl ? q : nl - 1) * in_pitch;
-		if (IN16) ld_cached_16(row, raw[q]);
-		else ld_cached_8(row, raw[q]);
-		vl[q] = ld_sample_if<IB>(row - IB, L.has_left);
-		vr[q] = ld_sample_if<IB>(row + kSamplesPerLane * IB, L.has_right && right_in_picture);
+		if (active) {
+			if (IN16) ld_global_16(row, raw[q]);
+			else ld_global_8(row, raw[q]);
+		}
+		vl[q] = ld_sample_if<IB>(row - IB, mem_left);
+		vr[q] = ld_sample_if<IB>(row + kSamplesPerLane * IB, mem_right);
 	}
 
 	const int bank = c ? 1 : 0;
@@ -251,15 +285,17 @@ VFGS_HD void process_task_gather(const FgsParams& p, smem_addr_t luts, smem_addr
 			int w_cur = 0, w_up = 0, ru = 0;
 			if (q == 0 && ovl) { w_cur = ysh ? 20 : 12; w_up = ysh ? 20 : 24; ru = (16 >> ysh) * L.stride; }
 			if (q == 1 && ovl && !ysh) { w_cur = 24; w_up = 12; ru = 17 * L.stride; }
-			gather_line<IN16, OUT8>(L, U, rc, w_cur, w_up, ru, p.bs, raw[q], vl[q], vr[q], w);
+			uint32_t nl_s, nr_s;
+			neighbour_samples<IN16>(raw[q], lane, vl[q], vr[q], right_in_picture, nl_s, nr_s);
+			gather_line<IN16, OUT8>(L, U, rc, w_cur, w_up, ru, p.bs, raw[q], nl_s, nr_s, w);
 			const bool more = line + kFastLB < nl;
-			if (IN16) ld_cached_16_if(nxt, raw[q], more);
-			else ld_cached_8_if(nxt, raw[q], more);
+			if (IN16) ld_global_16_if(nxt, raw[q], more && active);
+			else ld_global_8_if(nxt, raw[q], more && active);
 			if (more) {
-				vl[q] = ld_sample_if<IB>(nxt - IB, L.has_left);
-				vr[q] = ld_sample_if<IB>(nxt + kSamplesPerLane * IB, L.has_right && right_in_picture);
+				vl[q] = ld_sample_if<IB>(nxt - IB, mem_left);
+				vr[q] = ld_sample_if<IB>(nxt + kSamplesPerLane * IB, mem_right);
 			}
-			if (line < nl) {
+			if (line < nl && active) {
 				if (OB == 2) st_global_16(dst, w);
 				else st_global_8(dst, w);
 			}

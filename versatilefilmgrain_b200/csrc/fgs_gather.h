@@ -68,12 +68,22 @@ VFGS_HD void ld_cached_8_if(const uint8_t* p, uint32_t r[2], bool pred)
 	if (pred) memcpy(r, p, 8);
 #endif
 }
-// one sample (IB bytes wide) when pred is set, else 0
+// one sample (IB bytes wide) when pred is set, else 0; volatile so that it is issued where it is
+// written (a batch ahead of its use) instead of being sunk next to the use
 template <int IB>
 VFGS_HD uint32_t ld_sample_if(const uint8_t* p, bool pred)
 {
+#if defined(__CUDA_ARCH__)
+	uint32_t v = 0;
+	if (IB == 2)
+		asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.u16 %0, [%1];\n\t}" : "+r"(v) : "l"(p), "r"((uint32_t)pred));
+	else
+		asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.u8 %0, [%1];\n\t}" : "+r"(v) : "l"(p), "r"((uint32_t)pred));
+	return v;
+#else
 	if (!pred) return 0;
 	return IB == 2 ? (uint32_t)*(const uint16_t*)p : (uint32_t)*p;
+#endif
 }
 
 #if defined(__CUDA_ARCH__)
@@ -239,7 +249,7 @@ VFGS_HD void process_task_gather(const FgsParams& p, smem_addr_t luts, smem_addr
 	const bool mem_left = L.has_left && (kHaloFromMemory || lane == 0);
 	const bool mem_right = L.has_right && right_in_picture && (kHaloFromMemory || lane == 31);
 
-	uint32_t raw[kFastLB][4] = {}, vl[kFastLB], vr[kFastLB];
+	uint32_t raw[kFastLB][4] = {}, nbr[kFastLB]; // nbr: left | right << 16 neighbour samples fetched from memory
 #pragma unroll
 	for (int q = 0; q < kFastLB; q++) {
 		const uint8_t* row = src + (q < nl ? q : nl - 1) * in_pitch;
@@ -247,8 +257,7 @@ VFGS_HD void process_task_gather(const FgsParams& p, smem_addr_t luts, smem_addr
 			if (IN16) ld_global_16(row, raw[q]);
 			else ld_global_8(row, raw[q]);
 		}
-		vl[q] = ld_sample_if<IB>(row - IB, mem_left);
-		vr[q] = ld_sample_if<IB>(row + kSamplesPerLane * IB, mem_right);
+		nbr[q] = ld_sample_if<IB>(row - IB, mem_left) | (ld_sample_if<IB>(row + kSamplesPerLane * IB, mem_right) << 16);
 	}
 
 	const int bank = c ? 1 : 0;
@@ -286,15 +295,12 @@ VFGS_HD void process_task_gather(const FgsParams& p, smem_addr_t luts, smem_addr
 			if (q == 0 && ovl) { w_cur = ysh ? 20 : 12; w_up = ysh ? 20 : 24; ru = (16 >> ysh) * L.stride; }
 			if (q == 1 && ovl && !ysh) { w_cur = 24; w_up = 12; ru = 17 * L.stride; }
 			uint32_t nl_s, nr_s;
-			neighbour_samples<IN16>(raw[q], lane, vl[q], vr[q], right_in_picture, nl_s, nr_s);
+			neighbour_samples<IN16>(raw[q], lane, nbr[q] & 0xffffu, nbr[q] >> 16, right_in_picture, nl_s, nr_s);
 			gather_line<IN16, OUT8>(L, U, rc, w_cur, w_up, ru, p.bs, raw[q], nl_s, nr_s, w);
 			const bool more = line + kFastLB < nl;
 			if (IN16) ld_global_16_if(nxt, raw[q], more && active);
 			else ld_global_8_if(nxt, raw[q], more && active);
-			if (more) {
-				vl[q] = ld_sample_if<IB>(nxt - IB, mem_left);
-				vr[q] = ld_sample_if<IB>(nxt + kSamplesPerLane * IB, mem_right);
-			}
+			if (more) nbr[q] = ld_sample_if<IB>(nxt - IB, mem_left) | (ld_sample_if<IB>(nxt + kSamplesPerLane * IB, mem_right) << 16);
 			if (line < nl && active) {
 				if (OB == 2) st_global_16(dst, w);
 				else st_global_8(dst, w);

@@ -236,7 +236,7 @@ int launch_apply(const FgsParams& p, cudaStream_t stream, KernelKind kind = kGen
 	} else if (kind == kGather) {
 		kern = p.in_bytes == 1 ? fgs_apply_gather_kernel<false, false>
 		     : p.out_bytes == 1 ? fgs_apply_gather_kernel<true, true> : fgs_apply_gather_kernel<true, false>;
-		threads = kFastThreads; smem = gather_smem;
+		threads = kGatherThreads; smem = gather_smem;
 		if (smem > c.gather_smem_attr) {
 			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_gather_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_gather_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

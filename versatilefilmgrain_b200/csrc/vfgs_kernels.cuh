@@ -144,8 +144,11 @@ fgs_apply_fast_kernel(const __grid_constant__ FgsParams p)
 // Gather path: components with sample-adaptive pattern selection (fgs_gather.h). Shared memory: one
 // per-lane replicated LUT (32 KB, entry = scale | slot byte offset << 8) per gather component, each on a
 // 32 KB boundary, then the general table image (compact LUTs + pattern slots) brought in by one bulk copy.
+constexpr int kGatherThreads = 384; // 2 CTAs per SM at up to 80 registers: the gather path carries more per-lane state
+constexpr int kGatherWarps = kGatherThreads / 32;
+
 template <bool IN16, bool OUT8>
-__global__ void __launch_bounds__(kFastThreads, 2)
+__global__ void __launch_bounds__(kGatherThreads, 2)
 fgs_apply_gather_kernel(const __grid_constant__ FgsParams p)
 {
 	extern __shared__ __align__(128) uint8_t smem[];
@@ -166,7 +169,7 @@ fgs_apply_gather_kernel(const __grid_constant__ FgsParams p)
 		const uint16_t* compact = (const uint16_t*)(img_ptr + p.lut_off) + c * 256; // scale | slot << 8
 		uint32_t* lut = (uint32_t*)(lut_ptr + p.glut_index[c] * kLutBytes);
 		const uint32_t slot_bytes = (uint32_t)p.pat_size[c ? 1 : 0];
-		for (int i = threadIdx.x; i < 256 * 32; i += kFastThreads) {
+		for (int i = threadIdx.x; i < 256 * 32; i += kGatherThreads) {
 			const uint32_t e = compact[i >> 5];
 			lut[i] = (e & 0xffu) | (((e >> 8) * slot_bytes) << 8);
 		}
@@ -175,8 +178,8 @@ fgs_apply_gather_kernel(const __grid_constant__ FgsParams p)
 
 	const int lane = threadIdx.x & 31;
 	const smem_addr_t luts = smem_addr(lut_ptr), img = smem_addr(img_ptr);
-	const long long stride = (long long)gridDim.x * kFastWarps;
-	for (long long task = (long long)blockIdx.x * kFastWarps + (threadIdx.x >> 5); task < p.total_tasks; task += stride)
+	const long long stride = (long long)gridDim.x * kGatherWarps;
+	for (long long task = (long long)blockIdx.x * kGatherWarps + (threadIdx.x >> 5); task < p.total_tasks; task += stride)
 		process_task_gather<IN16, OUT8>(p, luts, img, (uint32_t)task, lane);
 }
 

@@ -249,7 +249,8 @@ VFGS_HD void process_task_gather(const FgsParams& p, smem_addr_t luts, smem_addr
 	const bool mem_left = L.has_left && (kHaloFromMemory || lane == 0);
 	const bool mem_right = L.has_right && right_in_picture && (kHaloFromMemory || lane == 31);
 
-	uint32_t raw[kFastLB][4] = {}, nbr[kFastLB]; // nbr: left | right << 16 neighbour samples fetched from memory
+	uint32_t raw[kFastLB][4] = {}, vl[kFastLB], vr[kFastLB]; // vl/vr: neighbour samples fetched from memory (kept apart:
+	                                                          // combining them would wait for the loads just issued)
 #pragma unroll
 	for (int q = 0; q < kFastLB; q++) {
 		const uint8_t* row = src + (q < nl ? q : nl - 1) * in_pitch;
@@ -257,7 +258,8 @@ VFGS_HD void process_task_gather(const FgsParams& p, smem_addr_t luts, smem_addr
 			if (IN16) ld_global_16(row, raw[q]);
 			else ld_global_8(row, raw[q]);
 		}
-		nbr[q] = ld_sample_if<IB>(row - IB, mem_left) | (ld_sample_if<IB>(row + kSamplesPerLane * IB, mem_right) << 16);
+		vl[q] = ld_sample_if<IB>(row - IB, mem_left);
+		vr[q] = ld_sample_if<IB>(row + kSamplesPerLane * IB, mem_right);
 	}
 
 	const int bank = c ? 1 : 0;
@@ -295,12 +297,13 @@ VFGS_HD void process_task_gather(const FgsParams& p, smem_addr_t luts, smem_addr
 			if (q == 0 && ovl) { w_cur = ysh ? 20 : 12; w_up = ysh ? 20 : 24; ru = (16 >> ysh) * L.stride; }
 			if (q == 1 && ovl && !ysh) { w_cur = 24; w_up = 12; ru = 17 * L.stride; }
 			uint32_t nl_s, nr_s;
-			neighbour_samples<IN16>(raw[q], lane, nbr[q] & 0xffffu, nbr[q] >> 16, right_in_picture, nl_s, nr_s);
+			neighbour_samples<IN16>(raw[q], lane, vl[q], vr[q], right_in_picture, nl_s, nr_s);
 			gather_line<IN16, OUT8>(L, U, rc, w_cur, w_up, ru, p.bs, raw[q], nl_s, nr_s, w);
 			const bool more = line + kFastLB < nl;
 			if (IN16) ld_global_16_if(nxt, raw[q], more && active);
 			else ld_global_8_if(nxt, raw[q], more && active);
-			if (more) nbr[q] = ld_sample_if<IB>(nxt - IB, mem_left) | (ld_sample_if<IB>(nxt + kSamplesPerLane * IB, mem_right) << 16);
+			vl[q] = ld_sample_if<IB>(nxt - IB, mem_left && more);
+			vr[q] = ld_sample_if<IB>(nxt + kSamplesPerLane * IB, mem_right && more);
 			if (line < nl && active) {
 				if (OB == 2) st_global_16(dst, w);
 				else st_global_8(dst, w);

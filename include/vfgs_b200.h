@@ -103,6 +103,9 @@ int vfgs_b200_kernel_time(double* total_ms, uint64_t* launches);
  * everything, 2 = gather kernel wherever it can run. All three are CUDA paths. */
 void vfgs_b200_force_general_kernel(int mode);
 
+/* Frame pipeline behind include/yuv.h: out[0] = frames processed, out[1] = batches flushed. */
+void vfgs_b200_pipeline_stats(unsigned long long out[2]);
+
 /* Geometry of the last grain kernel launch: out[0]=grid, out[1]=block, out[2]=dynamic smem bytes,
  * out[3]=SM count of the bound device, out[4]=which grain kernels the last frame call launched
  * (bit 0 fast, bit 1 general, bit 2 gather). */

@@ -27,7 +27,7 @@ B200_SYMBOLS = (
     "vfgs_b200_add_grain_frames_host", "vfgs_b200_skip_frames", "vfgs_b200_get_lfsr",
     "vfgs_b200_set_lfsr", "vfgs_b200_host_alloc", "vfgs_b200_host_free", "vfgs_b200_launch_count",
     "vfgs_b200_last_launch", "vfgs_b200_get_state", "vfgs_b200_kernel_timing", "vfgs_b200_kernel_time",
-    "vfgs_b200_force_general_kernel",
+    "vfgs_b200_force_general_kernel", "vfgs_b200_pipeline_stats",
 )
 
 

@@ -16,8 +16,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvfgs_b200.so")
 SOURCES = [os.path.join(CSRC, "vfgs_b200.cu")]
-HEADERS = [os.path.join(CSRC, n) for n in ("vfgs_core.h", "fgs_task.h", "vfgs_kernels.cuh")] + [
-    os.path.join(os.path.dirname(HERE), "include", n) for n in ("vfgs_hw.h", "vfgs_b200.h")]
+HEADERS = [os.path.join(CSRC, n) for n in ("vfgs_core.h", "fgs_task.h", "fgs_fast.h", "fgs_gather.h", "vfgs_tables.h",
+                                            "vfgs_kernels.cuh", "yuv_pipeline.h")] + [
+    os.path.join(os.path.dirname(HERE), "include", n) for n in ("vfgs_hw.h", "vfgs_b200.h", "yuv.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -53,5 +54,30 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+REF_SRC = os.environ.get("VFGS_REF_SRC", "/root/reference/src")
+CLI = os.path.join(os.path.dirname(HERE), "build", "vfgs_b200")
+
+
+def build_cli(force: bool = False) -> str | None:
+    """The reference CLI on the CUDA back end: the UNMODIFIED src/vfgs_main.c and src/vfgs_fw.c,
+    compiled where they lie (nothing is copied into the repo), linked against libvfgs_b200.so, which
+    provides both the vfgs_hw.h layer and the batched yuv.h layer. Only possible where the reference
+    tree is mounted; elsewhere the prebuilt build/vfgs_b200 (git-ignored, travels with the snapshot)
+    is used. Returns the path, or None if it can be neither built nor found."""
+    srcs = [os.path.join(REF_SRC, n) for n in ("vfgs_main.c", "vfgs_fw.c")]
+    if not all(os.path.exists(f) for f in srcs):
+        return CLI if os.path.exists(CLI) else None
+    build()
+    if not force and os.path.exists(CLI) and os.path.getmtime(CLI) >= max(os.path.getmtime(f) for f in srcs + [LIB]):
+        return CLI
+    os.makedirs(os.path.dirname(CLI), exist_ok=True)
+    cmd = ["gcc", "-O2", "-w", "-I", REF_SRC] + srcs + ["-o", CLI, "-L", HERE, "-lvfgs_b200", "-Wl,-rpath,$ORIGIN/../versatilefilmgrain_b200"]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    if out.returncode != 0:
+        raise RuntimeError("CLI link failed:\n" + " ".join(cmd) + "\n" + out.stdout + out.stderr)
+    return CLI
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_cli(force="--force" in sys.argv))

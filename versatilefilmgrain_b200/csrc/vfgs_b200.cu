@@ -12,6 +12,7 @@
 
 #include "../../include/vfgs_b200.h"
 #include "../../include/vfgs_hw.h"
+#include "../../include/yuv.h"
 #include "vfgs_kernels.cuh"
 #include "vfgs_tables.h"
 
@@ -79,6 +80,10 @@ HwState& hw()
 	if (!g_hw_init) { g_hw.power_on(); g_hw_init = true; }
 	return g_hw;
 }
+
+// frame pipeline hooks (yuv_pipeline.h, end of this file)
+void pipe_before_state_change();
+bool pipe_line(const void* Y, int y);
 
 int set_err(int code, const char* fmt, ...)
 {
@@ -355,6 +360,7 @@ extern "C" {
 
 void vfgs_set_luma_pattern(int index, int8_t* P) // vfgs_hw.c:314-318
 {
+	pipe_before_state_change();
 	REQUIRE(index >= 0 && index < VFGS_MAX_PATTERNS);
 	memcpy(hw().pattern[0][index], P, 64 * 64);
 	g_dirty = true;
@@ -362,6 +368,7 @@ void vfgs_set_luma_pattern(int index, int8_t* P) // vfgs_hw.c:314-318
 
 void vfgs_set_chroma_pattern(int index, int8_t* P) // vfgs_hw.c:320-325
 {
+	pipe_before_state_change();
 	REQUIRE(index >= 0 && index < VFGS_MAX_PATTERNS);
 	HwState& h = hw();
 	const int rows = 64 / h.csuby, src_stride = 64 / h.csuby, ncopy = 64 / h.csubx;
@@ -371,6 +378,7 @@ void vfgs_set_chroma_pattern(int index, int8_t* P) // vfgs_hw.c:320-325
 
 void vfgs_set_scale_lut(int c, uint8_t lut[]) // vfgs_hw.c:327-331
 {
+	pipe_before_state_change();
 	REQUIRE(c >= 0 && c < 3);
 	memcpy(hw().slut[c], lut, 256);
 	g_dirty = true;
@@ -378,6 +386,7 @@ void vfgs_set_scale_lut(int c, uint8_t lut[]) // vfgs_hw.c:327-331
 
 void vfgs_set_pattern_lut(int c, uint8_t lut[]) // vfgs_hw.c:333-337
 {
+	pipe_before_state_change();
 	REQUIRE(c >= 0 && c < 3);
 	// lut[i] >> 4 indexes pattern[..][9] in vfgs_hw.c:218; anything above slot 8 is out of bounds there
 	for (int i = 0; i < 256; i++) REQUIRE((lut[i] >> 4) < kSlots);
@@ -387,12 +396,14 @@ void vfgs_set_pattern_lut(int c, uint8_t lut[]) // vfgs_hw.c:333-337
 
 void vfgs_set_seed(uint32_t seed) // vfgs_hw.c:339-344
 {
+	pipe_before_state_change();
 	HwState& h = hw();
 	h.rnd = h.rnd_up = h.line_rnd = h.line_rnd_up = seed << 1;
 }
 
 void vfgs_set_scale_shift(int shift) // vfgs_hw.c:346-350
 {
+	pipe_before_state_change();
 	REQUIRE(shift >= 2 && shift < 8);
 	HwState& h = hw();
 	h.scale_shift = shift + 6 - h.bs;
@@ -400,6 +411,7 @@ void vfgs_set_scale_shift(int shift) // vfgs_hw.c:346-350
 
 void vfgs_set_depth(int depth) // vfgs_hw.c:352-362
 {
+	pipe_before_state_change();
 	REQUIRE(depth == 8 || depth == 10);
 	HwState& h = hw();
 	const int nbs = depth - 8;
@@ -410,6 +422,7 @@ void vfgs_set_depth(int depth) // vfgs_hw.c:352-362
 
 void vfgs_set_legal_range(int legal) // vfgs_hw.c:364-380
 {
+	pipe_before_state_change();
 	HwState& h = hw();
 	h.y_min = h.c_min = legal ? 16 : 0;
 	h.y_max = legal ? 235 : 255;
@@ -418,6 +431,7 @@ void vfgs_set_legal_range(int legal) // vfgs_hw.c:364-380
 
 void vfgs_set_chroma_subsampling(int subx, int suby) // vfgs_hw.c:382-388
 {
+	pipe_before_state_change();
 	REQUIRE(subx == 1 || subx == 2);
 	REQUIRE(suby == 1 || suby == 2);
 	HwState& h = hw();
@@ -429,6 +443,7 @@ void vfgs_set_chroma_subsampling(int subx, int suby) // vfgs_hw.c:382-388
 // reference's; the samples go through the same kernels as the frame entry points.
 void vfgs_add_grain_line(void* Y, void* U, void* V, int y, int width)
 {
+	if (pipe_line(Y, y)) return; // a slot of the frame pipeline (include/yuv.h): the whole frame is processed at flush time
 	HwState& h = hw();
 	Geometry g;
 	if (make_geometry(g, width, 16 * ((y >> 4) + 1), 0)) fatal("vfgs_add_grain_line");
@@ -680,3 +695,5 @@ void vfgs_b200_last_launch(int out[5])
 }
 
 } // extern "C"
+
+#include "yuv_pipeline.h"

@@ -89,6 +89,14 @@ extern "C" int emu_add_grain_frames(const void* state, const void* in, void* out
 	FgsParams p;
 	memset(&p, 0, sizeof(p));
 	fill_state_params(p, h, bi);
+	// window offsets of every block (the second table lfsr_states_kernel writes)
+	std::vector<uint16_t> woffs(states.size() * 4, 0);
+	{
+		const WoffParams wp = make_woff_params(p);
+		for (size_t i = 0; i < states.size(); i++)
+			for (int c = 0; c < 3; c++) woffs[i * 4 + c] = (uint16_t)window_offset(c, states[i], wp.off[c], wp.stride[c], wp.subx, wp.suby);
+	}
+	p.woffs = woffs.data();
 	p.nframes = nframes; p.nb = nb; p.R = R; p.row_begin = 0; p.rows = R;
 	p.y_begin = 0; p.y_end = height;
 	p.in_bytes = (int)isz; p.out_bytes = (int)osz;

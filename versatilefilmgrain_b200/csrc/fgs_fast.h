@@ -262,11 +262,13 @@ VFGS_HD void fast_line(const FastLane& L, int rc, int w_cur, int w_up, const Fas
 	}
 }
 
-// Address of (block window, column) inside the shared image.
-VFGS_HD smem_addr_t window_addr(const FgsParams& p, smem_addr_t img, int c, uint32_t state, int col)
+// Byte offset, inside the fast image, of a block's pattern window for component c: the +pattern or
+// -pattern copy according to the block's sign, row oy, column ox. Precomputed per block by
+// lfsr_states_kernel (FgsParams::woffs), so a lane only adds its column and the line's row pitch.
+VFGS_HD uint32_t window_offset(int c, uint32_t state, const int off[2], int stride, int subx, int suby)
 {
-	const BlockOfs o = decode_offsets(c, state, p.subx, p.suby);
-	return img + (smem_addr_t)(p.fpat_off[c][o.sign < 0 ? 1 : 0] + o.oy * p.fpat_stride[c] + o.ox + col);
+	const BlockOfs o = decode_offsets(c, state, subx, suby);
+	return (uint32_t)(off[o.sign < 0 ? 1 : 0] + o.oy * stride + o.ox);
 }
 
 constexpr int kFastLB = 4; // lines in flight per lane
@@ -315,21 +317,21 @@ VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, smem_addr_t img
 	L.lo2 = (uint32_t)p.lo[c] * 0x00010001u; L.hi2 = (uint32_t)p.hi[c] * 0x00010001u;
 
 	const int srow = t.r - p.stream_row0;
-	const uint32_t* row_cur = p.states + ((long long)t.f * p.stream_rows + srow) * p.spitch + 1 + b;
-	L.own = window_addr(p, img, c, row_cur[0], i0);
+	const uint16_t* w_cur = p.woffs + (((long long)t.f * p.stream_rows + srow) * p.spitch + 1 + b) * 4 + c;
+	L.own = img + (smem_addr_t)(w_cur[0] + i0);
 	L.lh = L.rh = L.own;
-	if (L.has_left) L.lh = window_addr(p, img, c, row_cur[-1], n - 1);
-	if (L.has_right) L.rh = window_addr(p, img, c, row_cur[1], 0);
+	if (L.has_left) L.lh = img + (smem_addr_t)(w_cur[-4] + n - 1);
+	if (L.has_right) L.rh = img + (smem_addr_t)w_cur[4];
 
 	// the first lines of a stripe overlap the block-row above (never in the first stripe, y <= 15)
 	FastUp U;
 	U.own = U.lh = U.rh = L.own;
 	bool ovl = t.r > 0;
 	if (ovl) {
-		const uint32_t* row_up = row_cur - p.spitch;
-		U.own = window_addr(p, img, c, row_up[0], i0);
-		if (L.has_left) U.lh = window_addr(p, img, c, row_up[-1], n - 1);
-		if (L.has_right) U.rh = window_addr(p, img, c, row_up[1], 0);
+		const uint16_t* w_up = w_cur - p.spitch * 4;
+		U.own = img + (smem_addr_t)(w_up[0] + i0);
+		if (L.has_left) U.lh = img + (smem_addr_t)(w_up[-4] + n - 1);
+		if (L.has_right) U.rh = img + (smem_addr_t)w_up[4];
 	}
 
 	int rc = 0;

@@ -102,9 +102,9 @@ struct TaskGeom {
 VFGS_HD TaskGeom decode_task(const FgsParams& p, uint32_t task)
 {
 	TaskGeom g;
-	const uint32_t fr = task / (uint32_t)p.tasks_per_stripe;
+	const uint32_t fr = fastdiv(task, p.div_tps);
 	int q = (int)(task - fr * (uint32_t)p.tasks_per_stripe);
-	g.f = (int)(fr / (uint32_t)p.rows);
+	g.f = (int)fastdiv(fr, p.div_rows);
 	g.r = p.row_begin + (int)(fr - (uint32_t)g.f * (uint32_t)p.rows);
 	if (q < p.nseg[0]) { g.c = 0; g.seg = q; }
 	else if (q < p.nseg[0] + p.nseg[1]) { g.c = 1; g.seg = q - p.nseg[0]; }

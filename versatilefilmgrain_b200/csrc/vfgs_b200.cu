@@ -14,7 +14,6 @@
 #include "../../include/vfgs_hw.h"
 #include "../../include/yuv.h"
 #include "vfgs_kernels.cuh"
-#include "vfgs_tables.h"
 
 using namespace vfgs;
 
@@ -29,6 +28,7 @@ struct Slot { // one stage of the host pipeline
 	cudaEvent_t h2d_done = nullptr, k_done = nullptr, d2h_done = nullptr;
 };
 constexpr int kPipeSlots = 3;
+constexpr size_t kBlockTableBytes = sizeof(uint32_t) + 4 * sizeof(uint16_t); // per block: LFSR register + window offsets
 
 struct Context {
 	bool ready = false;
@@ -276,11 +276,11 @@ int launch_apply(const FgsParams& p, cudaStream_t stream, KernelKind kind = kGen
 	return VFGS_B200_OK;
 }
 
-int launch_streams(uint32_t epoch, uint32_t* d_streams, int nframes, const Geometry& g, uint64_t frame0, cudaStream_t stream)
+int launch_streams(uint32_t epoch, uint32_t* d_streams, uint16_t* d_woffs, const FgsParams& p, int nframes, const Geometry& g, uint64_t frame0, cudaStream_t stream)
 {
 	const long long warps = (long long)nframes * g.R;
 	const int grid = (int)((warps * 32 + kCtaThreads - 1) / kCtaThreads);
-	lfsr_states_kernel<<<grid, kCtaThreads, 0, stream>>>(epoch, g_ctx.d_pow2, d_streams, nframes, g.R, g.nb, g.spitch, frame0);
+	lfsr_states_kernel<<<grid, kCtaThreads, 0, stream>>>(epoch, g_ctx.d_pow2, d_streams, d_woffs, make_woff_params(p), nframes, g.R, g.nb, g.spitch, frame0);
 	CUDA_TRY(cudaGetLastError());
 	g_launches++;
 	return VFGS_B200_OK;
@@ -321,9 +321,11 @@ int run_frames_device(const vfgs_b200_planes& in, const vfgs_b200_planes& out, i
 		p.comp[c].width = c ? g.cw : g.width;
 		p.comp[c].lines = c ? g.ch : g.height;
 	}
-	p.states = d_streams; p.stream_rows = g.R; p.stream_row0 = 0;
+	// one allocation holds both per-block tables: uint32 registers, then 4 x uint16 window offsets
+	uint16_t* d_woffs = (uint16_t*)(d_streams + (((size_t)n * g.R * g.spitch + 3) & ~(size_t)3)); // 16-byte aligned
+	p.states = d_streams; p.woffs = d_woffs; p.stream_rows = g.R; p.stream_row0 = 0;
 	finish_tasks(p);
-	if (int rc = launch_streams(epoch, d_streams, n, g, frame0, stream)) return rc;
+	if (int rc = launch_streams(epoch, d_streams, d_woffs, p, n, g, frame0, stream)) return rc;
 	// every component goes to the cheapest kernel that can serve it (plan_launches)
 	g_ctx.last_launch[4] = 0;
 	LaunchPlan lp;
@@ -537,7 +539,7 @@ int vfgs_b200_add_grain_planes_device(const vfgs_b200_planes* in, const vfgs_b20
 	cudaStream_t st = (cudaStream_t)stream;
 	if (c.used_stream && c.last_stream != st) CUDA_TRY(cudaStreamSynchronize(c.last_stream)); // d_streams is shared
 	c.last_stream = st; c.used_stream = true;
-	if (int rc = grow(c.d_streams, c.streams_cap, (size_t)nframes * g.R * g.spitch * sizeof(uint32_t))) return rc;
+	if (int rc = grow(c.d_streams, c.streams_cap, (size_t)nframes * g.R * g.spitch * kBlockTableBytes + 16)) return rc;
 	if (int rc = run_frames_device(*in, *out, nframes, g, hw().line_rnd, 0, c.d_streams, st)) return rc;
 	advance_registers(g, (uint64_t)nframes);
 	return VFGS_B200_OK;
@@ -579,7 +581,7 @@ int vfgs_b200_add_grain_frames_host(const void* in, void* out, int nframes, int 
 		Slot& s = c.slot[idx % kPipeSlots];
 		if (int rc = grow(s.d_in, s.in_cap, (size_t)per * g.in_frame_bytes)) return rc;
 		if (int rc = grow(s.d_out, s.out_cap, (size_t)per * g.out_frame_bytes)) return rc;
-		if (int rc = grow(s.d_streams, s.streams_cap, (size_t)per * g.R * g.spitch * sizeof(uint32_t))) return rc;
+		if (int rc = grow(s.d_streams, s.streams_cap, (size_t)per * g.R * g.spitch * kBlockTableBytes + 16)) return rc;
 		// the slot's previous chunk must have left the device before its buffers are overwritten
 		if (idx >= kPipeSlots) {
 			CUDA_TRY(cudaStreamWaitEvent(c.s_h2d, s.k_done, 0));   // d_in free once its kernel is done

@@ -114,6 +114,30 @@ VFGS_HD BlockOfs decode_offsets(int c, uint32_t s, int subx, int suby)
 	return o;
 }
 
+// ------------------------------------------------------------------------------------ division by launch constants
+// q = n / d for n < 2^31 with a precomputed 33-bit reciprocal (Granlund-Montgomery round-up method):
+// two instructions instead of the ~25 of a 32-bit hardware-less division, once per warp-task.
+struct FastDiv {
+	uint32_t m;
+	int s;
+};
+inline FastDiv make_fastdiv(uint32_t d)
+{
+	FastDiv f;
+	f.s = 0;
+	while ((1ull << f.s) < d) f.s++;
+	f.m = (uint32_t)((((1ull << f.s) - d) << 32) / d + 1);
+	return f;
+}
+VFGS_HD uint32_t fastdiv(uint32_t n, FastDiv f)
+{
+#if defined(__CUDA_ARCH__)
+	return (__umulhi(f.m, n) + n) >> f.s;
+#else
+	return (uint32_t)((((uint64_t)f.m * n) >> 32) + n) >> f.s;
+#endif
+}
+
 // ------------------------------------------------------------------------------------ launch block
 struct Plane {
 	const uint8_t* in;
@@ -142,6 +166,7 @@ struct FgsParams {
 	int lo[3], hi[3];       // clip range per component, already << bs
 	int uniform_pi[3];      // pattern slot when the pattern LUT selects a single slot, else -1
 	int nseg[3], tasks_per_stripe;
+	FastDiv div_tps, div_rows; // reciprocals of tasks_per_stripe and rows
 	// table image ("blob") copied to shared memory by every CTA
 	const uint8_t* blob;
 	int blob_bytes;
@@ -163,6 +188,9 @@ struct FgsParams {
 	// the register of block b of that block-row (words 0 and nb + 1 are padding for the b-1 / b+1 reads)
 	const uint32_t* states;
 	int spitch, stream_rows, stream_row0;
+	// same indexing, four uint16 per block: byte offset (inside the fast image, block sign folded in) of the
+	// block's pattern window for Y, U, V (fast path only; written by lfsr_states_kernel)
+	const uint16_t* woffs;
 };
 
 } // namespace vfgs

@@ -12,7 +12,7 @@
 //                        loads and stores.
 #pragma once
 #include <cuda_runtime.h>
-#include "fgs_gather.h"
+#include "vfgs_tables.h"
 
 namespace vfgs {
 
@@ -54,13 +54,15 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gm
 
 // ---- LFSR registers per block -------------------------------------------------------------
 // states[(f * R + r) * spitch + 1 + b] = LFSR register of block b of block-row r of frame frame0 + f
-// (words 0 and nb + 1 of a row are padding). One warp per (frame, block-row): jump the epoch register
+// (words 0 and nb + 1 of a row are padding); woffs, when not null, gets the same blocks' pattern-window
+// offsets for the fast path (four uint16 per block: Y, U, V, unused). One warp per (frame, block-row): jump the epoch register
 // ahead by t = ((frame0 + f) (R - 1) + r) nb steps with the matrix powers pow2 (JumpTable as
 // uint32[64][32]; lane i owns output bit i, a ballot assembles the word), then walk the row 32 steps
 // at a time: consecutive blocks are consecutive 32-bit windows of one bit-stream, so lane l takes
 // window l of every {word k, word k+1} pair and the 32 registers go out as one coalesced store.
 __global__ void __launch_bounds__(kCtaThreads)
 lfsr_states_kernel(uint32_t epoch_state, const uint32_t* __restrict__ pow2, uint32_t* __restrict__ states,
+                   uint16_t* __restrict__ woffs, const WoffParams wp,
                    int nframes, int R, int nb, int spitch, unsigned long long frame0)
 {
 	const int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
@@ -77,7 +79,17 @@ lfsr_states_kernel(uint32_t epoch_state, const uint32_t* __restrict__ pow2, uint
 	if (lane == 0) { dst[0] = 0; dst[nb + 1] = 0; }
 	for (int b0 = 0; b0 < nb; b0 += 32) {
 		const uint32_t next = __ballot_sync(0xffffffffu, __popc(step32 & s) & 1);
-		if (b0 + lane < nb) dst[1 + b0 + lane] = __funnelshift_r(s, next, lane);
+		if (b0 + lane < nb) {
+			const uint32_t st = __funnelshift_r(s, next, lane);
+			dst[1 + b0 + lane] = st;
+			if (woffs) { // pattern-window offsets of the block for the fast path, one 8-byte store
+				uint32_t o[3];
+				for (int c = 0; c < 3; c++) o[c] = window_offset(c, st, wp.off[c], wp.stride[c], wp.subx, wp.suby);
+				uint2 v;
+				v.x = o[0] | (o[1] << 16); v.y = o[2];
+				*(uint2*)(woffs + ((size_t)warp * spitch + 1 + b0 + lane) * 4) = v;
+			}
+		}
 		s = next;
 	}
 }

@@ -139,6 +139,8 @@ inline void finish_tasks(FgsParams& p)
 	}
 	p.tasks_per_stripe = p.nseg[0] + p.nseg[1] + p.nseg[2];
 	p.total_tasks = (long long)p.nframes * p.rows * p.tasks_per_stripe;
+	p.div_tps = make_fastdiv((uint32_t)(p.tasks_per_stripe > 0 ? p.tasks_per_stripe : 1));
+	p.div_rows = make_fastdiv((uint32_t)(p.rows > 0 ? p.rows : 1));
 }
 
 // Which grain kernel serves which component of a whole-frame launch:
@@ -185,7 +187,20 @@ inline void plan_launches(const FgsParams& p, const TableInfo& bi, int mode, boo
 	for (FgsParams* q : {&lp.fast, &lp.gather, &lp.general}) {
 		q->tasks_per_stripe = q->nseg[0] + q->nseg[1] + q->nseg[2];
 		q->total_tasks = (long long)q->nframes * q->rows * q->tasks_per_stripe;
+		q->div_tps = make_fastdiv((uint32_t)(q->tasks_per_stripe > 0 ? q->tasks_per_stripe : 1));
 	}
+}
+
+// What lfsr_states_kernel needs to turn a block register into the fast path's window offsets.
+struct WoffParams {
+	int off[3][2], stride[3], subx, suby;
+};
+inline WoffParams make_woff_params(const FgsParams& p)
+{
+	WoffParams w;
+	for (int c = 0; c < 3; c++) { w.off[c][0] = p.fpat_off[c][0]; w.off[c][1] = p.fpat_off[c][1]; w.stride[c] = p.fpat_stride[c]; }
+	w.subx = p.subx; w.suby = p.suby;
+	return w;
 }
 
 } // namespace vfgs

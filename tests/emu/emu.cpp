@@ -89,13 +89,7 @@ extern "C" int emu_add_grain_frames(const void* state, const void* in, void* out
 	FgsParams p;
 	memset(&p, 0, sizeof(p));
 	fill_state_params(p, h, bi);
-	// window offsets of every block (the second table lfsr_states_kernel writes)
 	std::vector<uint16_t> woffs(states.size() * 4, 0);
-	{
-		const WoffParams wp = make_woff_params(p);
-		for (size_t i = 0; i < states.size(); i++)
-			for (int c = 0; c < 3; c++) woffs[i * 4 + c] = (uint16_t)window_offset(c, states[i], wp.off[c], wp.stride[c], wp.subx, wp.suby);
-	}
 	p.woffs = woffs.data();
 	p.nframes = nframes; p.nb = nb; p.R = R; p.row_begin = 0; p.rows = R;
 	p.y_begin = 0; p.y_end = height;
@@ -116,6 +110,11 @@ extern "C" int emu_add_grain_frames(const void* state, const void* in, void* out
 
 	LaunchPlan lp;
 	plan_launches(p, bi, mode, in == out, 227 * 1024, lp);
+	{ // window offsets of every block (the second table lfsr_states_kernel writes), in the serving kernel's format
+		const WoffParams wp = make_woff_params(p, lp.kind);
+		for (size_t i = 0; i < states.size(); i++)
+			for (int c = 0; c < 3; c++) woffs[i * 4 + c] = (uint16_t)window_offset(c, states[i], wp.off[c], wp.stride[c], wp.subx, wp.suby);
+	}
 	if (lp.any_fast) {
 		if (isz == 1) run_fast<false, false>(lp.fast, lut_ptr, img_ptr);
 		else if (osz == 1) run_fast<true, true>(lp.fast, lut_ptr, img_ptr);

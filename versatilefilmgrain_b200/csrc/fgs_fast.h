@@ -274,14 +274,12 @@ VFGS_HD uint32_t window_offset(int c, uint32_t state, const int off[2], int stri
 constexpr int kFastLB = 4; // lines in flight per lane
 
 template <bool IN16, bool OUT8, int NSH>
-VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, smem_addr_t img, const TaskGeom& t, int lane)
+VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, smem_addr_t img, const TaskGeom& t, int k0, int lane)
 {
 	const int c = t.c;
 	const Plane& pl = p.comp[c];
 	const int ysh = (c && p.suby > 1) ? 1 : 0;
 	constexpr int n = 1 << NSH;
-	const int k0 = t.seg * kSegSamples + lane * kSamplesPerLane;
-	if (k0 >= pl.width) return;
 
 	// component lines of this stripe (whole stripes only: the host sends partial line ranges to
 	// the general kernel)
@@ -361,12 +359,27 @@ VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, smem_addr_t img
 
 // Dispatch on the component's block size (16 samples: luma and non-subsampled chroma; 8: chroma
 // subsampled horizontally).
+// Fast-kernel task numbering: per frame the components one after the other; inside a component the
+// stripes' rows are one flat run of lane units (8 samples), 32 consecutive units per warp-task, so only
+// the very last task of a component can have idle lanes (a row need not be a multiple of 256 samples).
 template <bool IN16, bool OUT8>
 VFGS_HD void process_task_fast(const FgsParams& p, smem_addr_t lut, smem_addr_t img, uint32_t task, int lane)
 {
-	const TaskGeom t = decode_task(p, task);
-	if (t.c && p.subx > 1) fast_task_body<IN16, OUT8, 3>(p, lut, img, t, lane);
-	else fast_task_body<IN16, OUT8, 4>(p, lut, img, t, lane);
+	TaskGeom t;
+	t.f = (int)fastdiv(task, p.div_ftasks);
+	uint32_t q = task - (uint32_t)t.f * (uint32_t)p.ftasks_per_frame;
+	t.c = 0;
+	if (q >= (uint32_t)p.ftasks[0]) { q -= (uint32_t)p.ftasks[0]; t.c = 1; }
+	if (t.c == 1 && q >= (uint32_t)p.ftasks[1]) { q -= (uint32_t)p.ftasks[1]; t.c = 2; }
+	const uint32_t unit = q * 32u + (uint32_t)lane;
+	const uint32_t upr = (uint32_t)p.funits_per_row[t.c];
+	if (unit >= upr * (uint32_t)p.rows) return;
+	const uint32_t row = fastdiv(unit, p.div_funits[t.c]);
+	t.r = p.row_begin + (int)row;
+	t.seg = 0;
+	const int k0 = (int)(unit - row * upr) * kSamplesPerLane;
+	if (t.c && p.subx > 1) fast_task_body<IN16, OUT8, 3>(p, lut, img, t, k0, lane);
+	else fast_task_body<IN16, OUT8, 4>(p, lut, img, t, k0, lane);
 }
 
 } // namespace vfgs

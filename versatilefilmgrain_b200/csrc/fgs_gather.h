@@ -205,13 +205,12 @@ VFGS_HD void gather_line(const GatherLane& L, const GatherUp& U, int rc, int w_c
 	}
 }
 
-// Window address (without slot offset) and sign of a block.
-VFGS_HD smem_addr_t gather_window(const FgsParams& p, smem_addr_t img, int c, uint32_t state, int col, int& sign)
+// Window address (without slot offset) and sign of a block from its precomputed table entry
+// (FgsParams::woffs, gather format: oy * stride + ox, bit 15 = negative sign).
+VFGS_HD smem_addr_t gather_window(smem_addr_t bank, uint32_t entry, int col, int& sign)
 {
-	const BlockOfs o = decode_offsets(c, state, p.subx, p.suby);
-	sign = o.sign;
-	const int bank = c ? 1 : 0;
-	return img + (smem_addr_t)(p.gpat_off[bank] + o.oy * p.pat_stride[bank] + o.ox + col);
+	sign = (entry & 0x8000u) ? -1 : 1;
+	return bank + (smem_addr_t)((entry & 0x7fffu) + (uint32_t)col);
 }
 
 template <bool IN16, bool OUT8>
@@ -269,20 +268,21 @@ VFGS_HD void process_task_gather(const FgsParams& p, smem_addr_t luts, smem_addr
 	L.lo2 = (uint32_t)p.lo[c] * 0x00010001u; L.hi2 = (uint32_t)p.hi[c] * 0x00010001u;
 
 	const int srow = t.r - p.stream_row0;
-	const uint32_t* row_cur = p.states + ((long long)t.f * p.stream_rows + srow) * p.spitch + 1 + b;
-	L.own = gather_window(p, img, c, row_cur[0], i0, L.s_own);
+	const uint16_t* w_cur = p.woffs + (((long long)t.f * p.stream_rows + srow) * p.spitch + 1 + b) * 4 + c;
+	const smem_addr_t bank_addr = img + (smem_addr_t)p.gpat_off[bank];
+	L.own = gather_window(bank_addr, w_cur[0], i0, L.s_own);
 	L.lh = L.rh = L.own; L.s_l = L.s_r = 1;
-	if (L.has_left) L.lh = gather_window(p, img, c, row_cur[-1], n - 1, L.s_l);
-	if (L.has_right) L.rh = gather_window(p, img, c, row_cur[1], 0, L.s_r);
+	if (L.has_left) L.lh = gather_window(bank_addr, w_cur[-4], n - 1, L.s_l);
+	if (L.has_right) L.rh = gather_window(bank_addr, w_cur[4], 0, L.s_r);
 
 	GatherUp U;
 	U.own = U.lh = U.rh = L.own; U.s_own = U.s_l = U.s_r = 1;
 	bool ovl = t.r > 0;
 	if (ovl) {
-		const uint32_t* row_up = row_cur - p.spitch;
-		U.own = gather_window(p, img, c, row_up[0], i0, U.s_own);
-		if (L.has_left) U.lh = gather_window(p, img, c, row_up[-1], n - 1, U.s_l);
-		if (L.has_right) U.rh = gather_window(p, img, c, row_up[1], 0, U.s_r);
+		const uint16_t* w_up = w_cur - p.spitch * 4;
+		U.own = gather_window(bank_addr, w_up[0], i0, U.s_own);
+		if (L.has_left) U.lh = gather_window(bank_addr, w_up[-4], n - 1, U.s_l);
+		if (L.has_right) U.rh = gather_window(bank_addr, w_up[4], 0, U.s_r);
 	}
 
 	int rc = 0;

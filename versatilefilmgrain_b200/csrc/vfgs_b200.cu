@@ -276,11 +276,11 @@ int launch_apply(const FgsParams& p, cudaStream_t stream, KernelKind kind = kGen
 	return VFGS_B200_OK;
 }
 
-int launch_streams(uint32_t epoch, uint32_t* d_streams, uint16_t* d_woffs, const FgsParams& p, int nframes, const Geometry& g, uint64_t frame0, cudaStream_t stream)
+int launch_streams(uint32_t epoch, uint32_t* d_streams, uint16_t* d_woffs, const WoffParams& wp, int nframes, const Geometry& g, uint64_t frame0, cudaStream_t stream)
 {
 	const long long warps = (long long)nframes * g.R;
 	const int grid = (int)((warps * 32 + kCtaThreads - 1) / kCtaThreads);
-	lfsr_states_kernel<<<grid, kCtaThreads, 0, stream>>>(epoch, g_ctx.d_pow2, d_streams, d_woffs, make_woff_params(p), nframes, g.R, g.nb, g.spitch, frame0);
+	lfsr_states_kernel<<<grid, kCtaThreads, 0, stream>>>(epoch, g_ctx.d_pow2, d_streams, d_woffs, wp, nframes, g.R, g.nb, g.spitch, frame0);
 	CUDA_TRY(cudaGetLastError());
 	g_launches++;
 	return VFGS_B200_OK;
@@ -325,11 +325,11 @@ int run_frames_device(const vfgs_b200_planes& in, const vfgs_b200_planes& out, i
 	uint16_t* d_woffs = (uint16_t*)(d_streams + (((size_t)n * g.R * g.spitch + 3) & ~(size_t)3)); // 16-byte aligned
 	p.states = d_streams; p.woffs = d_woffs; p.stream_rows = g.R; p.stream_row0 = 0;
 	finish_tasks(p);
-	if (int rc = launch_streams(epoch, d_streams, d_woffs, p, n, g, frame0, stream)) return rc;
 	// every component goes to the cheapest kernel that can serve it (plan_launches)
 	g_ctx.last_launch[4] = 0;
 	LaunchPlan lp;
 	plan_launches(p, g_bi, g_kernel_mode, in.y == out.y, g_ctx.max_smem_optin - 1024, lp);
+	if (int rc = launch_streams(epoch, d_streams, d_woffs, make_woff_params(p, lp.kind), n, g, frame0, stream)) return rc;
 	if (lp.any_fast)
 		if (int rc = launch_apply(lp.fast, stream, kFast)) return rc;
 	if (lp.any_gather)

@@ -152,6 +152,7 @@ inline void finish_tasks(FgsParams& p)
 struct LaunchPlan {
 	FgsParams fast, gather, general;
 	bool any_fast, any_gather, any_general;
+	int kind[3];     // per component: 0 fast, 1 gather, 2 general kernel
 	int gather_smem; // dynamic shared memory of the gather launch
 };
 
@@ -159,7 +160,8 @@ inline void plan_launches(const FgsParams& p, const TableInfo& bi, int mode, boo
 {
 	lp.fast = lp.gather = lp.general = p;
 	lp.any_fast = lp.any_gather = lp.any_general = false;
-	int kind[3], ngather = 0;
+	int* kind = lp.kind;
+	int ngather = 0;
 	for (int c = 0; c < 3; c++) {
 		const bool aligned = p.comp[c].vec && (p.comp[c].width % kSamplesPerLane) == 0;
 		kind[c] = 2;
@@ -182,6 +184,18 @@ inline void plan_launches(const FgsParams& p, const TableInfo& bi, int mode, boo
 		if (kind[c] != 2) lp.general.nseg[c] = 0;
 		(kind[c] == 0 ? lp.any_fast : kind[c] == 1 ? lp.any_gather : lp.any_general) = true;
 	}
+	// the fast kernel numbers its tasks over flat runs of lane units (process_task_fast)
+	{
+		FgsParams& f = lp.fast;
+		f.ftasks_per_frame = 0;
+		for (int c = 0; c < 3; c++) {
+			f.funits_per_row[c] = kind[c] == 0 ? f.comp[c].width / kSamplesPerLane : 0;
+			f.ftasks[c] = (f.funits_per_row[c] * f.rows + 31) / 32;
+			f.ftasks_per_frame += f.ftasks[c];
+			f.div_funits[c] = make_fastdiv((uint32_t)(f.funits_per_row[c] > 0 ? f.funits_per_row[c] : 1));
+		}
+		f.div_ftasks = make_fastdiv((uint32_t)(f.ftasks_per_frame > 0 ? f.ftasks_per_frame : 1));
+	}
 	lp.gather.ngather = ngather;
 	lp.gather.gpat_off[0] = bi.pat_off[0]; lp.gather.gpat_off[1] = bi.pat_off[1];
 	for (FgsParams* q : {&lp.fast, &lp.gather, &lp.general}) {
@@ -189,16 +203,25 @@ inline void plan_launches(const FgsParams& p, const TableInfo& bi, int mode, boo
 		q->total_tasks = (long long)q->nframes * q->rows * q->tasks_per_stripe;
 		q->div_tps = make_fastdiv((uint32_t)(q->tasks_per_stripe > 0 ? q->tasks_per_stripe : 1));
 	}
+	lp.fast.total_tasks = (long long)lp.fast.nframes * lp.fast.ftasks_per_frame;
 }
 
-// What lfsr_states_kernel needs to turn a block register into the fast path's window offsets.
+// What lfsr_states_kernel needs to turn a block register into a pattern-window offset (FgsParams::woffs).
+// Per component the entry has the format of the kernel that serves it:
+//   fast    offset inside the fast image of the +pattern / -pattern copy (block sign folded in) + oy * stride + ox
+//   gather  oy * stride + ox inside a pattern slot, bit 15 set when the block sign is negative
 struct WoffParams {
+	int gather[3];
 	int off[3][2], stride[3], subx, suby;
 };
-inline WoffParams make_woff_params(const FgsParams& p)
+inline WoffParams make_woff_params(const FgsParams& p, const int kind[3])
 {
 	WoffParams w;
-	for (int c = 0; c < 3; c++) { w.off[c][0] = p.fpat_off[c][0]; w.off[c][1] = p.fpat_off[c][1]; w.stride[c] = p.fpat_stride[c]; }
+	for (int c = 0; c < 3; c++) {
+		w.gather[c] = kind[c] == 1;
+		if (w.gather[c]) { w.off[c][0] = 0; w.off[c][1] = 0x8000; w.stride[c] = p.pat_stride[c ? 1 : 0]; }
+		else { w.off[c][0] = p.fpat_off[c][0]; w.off[c][1] = p.fpat_off[c][1]; w.stride[c] = p.fpat_stride[c]; }
+	}
 	w.subx = p.subx; w.suby = p.suby;
 	return w;
 }

@@ -278,10 +278,20 @@ def run_b200_arm(args):
     # resident pool of distinct frames (uniform random codes: worst case for the LUT/pattern gathers)
     F = args.frames_per_step or int(max(8, min(1024, POOL_INPUT_BYTES // in_bytes)))
     gen = torch.Generator(device="cuda"); gen.manual_seed(1234 + rank)
-    if depth > 8:
-        src = torch.randint(0, 1 << depth, (F * samples,), dtype=torch.int16, device="cuda", generator=gen)
+    sdt = torch.int16 if depth > 8 else torch.uint8
+    if args.data == "uniform":
+        src = torch.randint(0, 1 << depth, (F * samples,), dtype=sdt, device="cuda", generator=gen)
     else:
-        src = torch.randint(0, 256, (F * samples,), dtype=torch.uint8, device="cuda", generator=gen)
+        # "natural": smooth horizontal gradient inside the legal range + small noise, so neighbouring samples
+        # mostly share LUT entries and pattern slots (best case for the gathers); generated frame by frame
+        src = torch.empty(F * samples, dtype=sdt, device="cuda")
+        lo, hi = 16 << (depth - 8), 235 << (depth - 8)
+        for f in range(F):
+            idx = torch.arange(samples, device="cuda", dtype=torch.float32)
+            base = lo + (hi - lo) * (0.5 + 0.45 * torch.sin(idx * (6.2831853 / w) + f * 0.37))
+            noise = torch.randint(-3, 4, (samples,), device="cuda", generator=gen)
+            src[f * samples:(f + 1) * samples] = (base.to(torch.int32) + noise).clamp_(0, (1 << depth) - 1).to(sdt)
+        del idx, base, noise
     dst = torch.empty(F * samples, dtype=torch.int16 if (od or depth) > 8 else torch.uint8, device="cuda")
     stream = torch.cuda.current_stream()
 
@@ -348,7 +358,7 @@ def run_b200_arm(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "int32", "data": "synthetic",
+        "dtype": "int32", "data": "synthetic" if args.data == "uniform" else "synthetic (smooth gradient + noise)",
         "config": workload_config(args.workload, F, f"inputs larger than L2: resident pool {F * (in_bytes + out_bytes) / 1e9:.1f} GB per GPU streamed once per step"),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": Fe * in_bytes, "d2h_bytes_per_step": Fe * out_bytes,
@@ -385,6 +395,8 @@ def main():
     ap.add_argument("--frames-per-step", type=int, default=0)
     ap.add_argument("--e2e-frames", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--data", default="uniform", choices=["uniform", "natural"],
+                    help="sample distribution of the synthetic frames (uniform random codes = worst case for the LUT/pattern gathers)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3  # timing rule: at least 3 warm-up steps

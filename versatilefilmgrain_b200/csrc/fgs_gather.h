@@ -156,20 +156,22 @@ VFGS_HD void gather_line(const GatherLane& L, const GatherUp& U, int rc, int w_c
 	gather_sample<7>(L, U, index_bits<IN16, 7>(raw), rc, wc_s, wu_s, ru, sc[7], g[7]);
 
 	// neighbours' edge samples (their own intensity selects their pattern slot), then the edge filter
-	if (L.has_left) {
-		const smem_addr_t off = (smem_addr_t)(lds32(L.lut | (smem_addr_t)(((vl >> in_shift) & 0xffu) << 7)) >> 8);
-		int h = lds_s8(L.lh + rc + off);
-		if (w_cur) h = (h * (w_cur * L.s_l) + lds_s8(U.lh + ru + off) * (w_up * U.s_l) + 16) >> 5;
-		else h *= L.s_l;
-		g[0] = (h + 3 * g[0] + g[1] + 2) >> 2;
-	}
-	// (g[0] above reads g[1] unfiltered; g[7] below reads g[6] unfiltered: a lane has 8 samples)
-	if (L.has_right) {
-		const smem_addr_t off = (smem_addr_t)(lds32(L.lut | (smem_addr_t)(((vr >> in_shift) & 0xffu) << 7)) >> 8);
-		int h = lds_s8(L.rh + rc + off);
-		if (w_cur) h = (h * (w_cur * L.s_r) + lds_s8(U.rh + ru + off) * (w_up * U.s_r) + 16) >> 5;
-		else h *= L.s_r;
-		g[7] = (g[6] + 3 * g[7] + h + 2) >> 2;
+	// (vfgs_hw.c:250-259). Computed unconditionally with harmless addresses when there is no neighbour
+	// (lh/rh fall back to the lane's own window) and selected at the end: straight-line code, no branches.
+	{
+		const smem_addr_t offl = (smem_addr_t)(lds32(L.lut | (smem_addr_t)(((vl >> in_shift) & 0xffu) << 7)) >> 8);
+		const smem_addr_t offr = (smem_addr_t)(lds32(L.lut | (smem_addr_t)(((vr >> in_shift) & 0xffu) << 7)) >> 8);
+		int hl = lds_s8(L.lh + rc + offl), hr = lds_s8(L.rh + rc + offr);
+		if (w_cur) {
+			hl = (hl * (w_cur * L.s_l) + lds_s8(U.lh + ru + offl) * (w_up * U.s_l) + 16) >> 5;
+			hr = (hr * (w_cur * L.s_r) + lds_s8(U.rh + ru + offr) * (w_up * U.s_r) + 16) >> 5;
+		} else {
+			hl *= L.s_l; hr *= L.s_r;
+		}
+		const int f0 = (hl + 3 * g[0] + g[1] + 2) >> 2; // both taps read unfiltered neighbours
+		const int f7 = (g[6] + 3 * g[7] + hr + 2) >> 2;
+		g[0] = L.has_left ? f0 : g[0];
+		g[7] = L.has_right ? f7 : g[7];
 	}
 
 	if (IN16) {

@@ -330,7 +330,7 @@ def run_b200_arm(args):
     value = world * F * args.steps / (ms_max * 1e-3)
 
     # end to end through the host entry point: pinned host buffers, H2D + kernels + D2H timed
-    Fe = args.e2e_frames or int(max(4, min(64, 4e8 // in_bytes)))
+    Fe = args.e2e_frames or int(max(8, min(128, 8e8 // in_bytes)))
     h_in = torch.empty(Fe * samples, dtype=src.dtype).pin_memory()
     h_in.copy_(src[: Fe * samples])
     h_out = torch.empty(Fe * samples, dtype=dst.dtype).pin_memory()
@@ -351,6 +351,14 @@ def run_b200_arm(args):
     e2e_value = world * Fe * e2e_steps / float(t.item())
 
     peak, peak_src = measured_peak_gbs()
+    traffic = traffic_src = None
+    try:  # DRAM bytes per frame of the grain kernel from the committed ncu capture of this workload
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f).get(args.workload) or {}
+        if t.get("dram_bytes_per_frame") and args.data == "uniform":
+            traffic, traffic_src = t["dram_bytes_per_frame"] * F, t["source"]
+    except Exception:
+        pass
     algo_bytes = F * (in_bytes + out_bytes)
     # grain kernels of one step (one launch for single-pattern configs, two when components split
     # between the fast and the gather kernel): algorithmic bytes of the step / their summed device time
@@ -365,7 +373,7 @@ def run_b200_arm(args):
                 "frames_per_step": Fe, "steps": e2e_steps, "host_buffers": "pinned"},
         "gpu_launches": int(gpu_launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "kernel": "+".join(hw.last_launch()["kernels"]), "launches_per_step": k_n / max(args.steps, 1),
                      "bytes_per_launch": algo_bytes, "avg_launch_ms": (k_ms / args.steps) if k_n else None,
                      "kernel_share_of_step": (k_ms / ms) if ms else None,

@@ -27,7 +27,7 @@ struct Slot { // one stage of the host pipeline
 	size_t in_cap = 0, out_cap = 0, streams_cap = 0;
 	cudaEvent_t h2d_done = nullptr, k_done = nullptr, d2h_done = nullptr;
 };
-constexpr int kPipeSlots = 3;
+constexpr int kPipeSlots = 4;
 constexpr size_t kBlockTableBytes = sizeof(uint32_t) + 4 * sizeof(uint16_t); // per block: LFSR register + window offsets
 
 struct Context {
@@ -569,7 +569,11 @@ int vfgs_b200_add_grain_frames_host(const void* in, void* out, int nframes, int 
 	if (c.used_stream) { CUDA_TRY(cudaStreamSynchronize(c.last_stream)); c.used_stream = false; }
 
 	// chunk = as many frames as fit ~64 MB of input; the ring has kPipeSlots chunks in flight
-	int per = (int)((64u << 20) / g.in_frame_bytes);
+	size_t chunk_bytes = 64u << 20;
+	int nslots = 3;
+	if (const char* e = getenv("VFGS_B200_CHUNK_MB")) { long v = atol(e); if (v > 0 && v <= 4096) chunk_bytes = (size_t)v << 20; }
+	if (const char* e = getenv("VFGS_B200_SLOTS")) { int v = atoi(e); if (v >= 2 && v <= kPipeSlots) nslots = v; }
+	int per = (int)(chunk_bytes / g.in_frame_bytes);
 	if (per < 1) per = 1;
 	if (per > nframes) per = nframes;
 	const uint32_t epoch = hw().line_rnd;
@@ -578,12 +582,12 @@ int vfgs_b200_add_grain_frames_host(const void* in, void* out, int nframes, int 
 	int idx = 0;
 	for (int f0 = 0; f0 < nframes; f0 += per, idx++) {
 		const int n = (nframes - f0 < per) ? nframes - f0 : per;
-		Slot& s = c.slot[idx % kPipeSlots];
+		Slot& s = c.slot[idx % nslots];
 		if (int rc = grow(s.d_in, s.in_cap, (size_t)per * g.in_frame_bytes)) return rc;
 		if (int rc = grow(s.d_out, s.out_cap, (size_t)per * g.out_frame_bytes)) return rc;
 		if (int rc = grow(s.d_streams, s.streams_cap, (size_t)per * g.R * g.spitch * kBlockTableBytes + 16)) return rc;
 		// the slot's previous chunk must have left the device before its buffers are overwritten
-		if (idx >= kPipeSlots) {
+		if (idx >= nslots) {
 			CUDA_TRY(cudaStreamWaitEvent(c.s_h2d, s.k_done, 0));   // d_in free once its kernel is done
 			CUDA_TRY(cudaStreamWaitEvent(c.s_k, s.d2h_done, 0));   // d_out free once copied back
 		}

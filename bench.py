@@ -218,6 +218,25 @@ def workload_config(name, frames_per_step, l2_note):
 
 
 # ------------------------------------------------------------------------------------- CUDA arm
+def bind_to_gpu_numa_node(index: int):
+    """Pin this process to the CPUs NVML reports as local to GPU `index` (same NUMA node / PCIe root), so
+    that the page-locked staging buffers it allocates afterwards are local too: with several ranks on one
+    host the H2D/D2H copies otherwise cross the socket interconnect. Returns a short description."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = (cpus & allowed) or allowed
+        os.sched_setaffinity(0, cpus)
+        return f"{len(cpus)} cpus local to gpu {index}"
+    except Exception as e:  # affinity is an optimisation, never a requirement
+        return f"not bound ({type(e).__name__})"
+
+
 def run_b200_arm(args):
     import torch
     import torch.distributed as dist
@@ -244,6 +263,7 @@ def run_b200_arm(args):
         cpu_baseline = {"value": arm.cores * fpw * len(tt) / sum(tt), "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
                         "sample": arm.describe() + f"; {len(tt)} timed steps after 1 warm-up"}
 
+    placement = bind_to_gpu_numa_node(local) if world > 1 else "single rank, not bound"
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -370,7 +390,7 @@ def run_b200_arm(args):
         "config": workload_config(args.workload, F, f"inputs larger than L2: resident pool {F * (in_bytes + out_bytes) / 1e9:.1f} GB per GPU streamed once per step"),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": Fe * in_bytes, "d2h_bytes_per_step": Fe * out_bytes,
-                "frames_per_step": Fe, "steps": e2e_steps, "host_buffers": "pinned"},
+                "frames_per_step": Fe, "steps": e2e_steps, "host_buffers": "pinned", "cpu_placement": placement},
         "gpu_launches": int(gpu_launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,

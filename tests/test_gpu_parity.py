@@ -287,6 +287,35 @@ def test_out_of_range_codes_and_minus_128_pattern(hw):
     assert np.array_equal(got, o.add_grain_frames(frames, n, w, h, 0))
 
 
+@pytest.mark.parametrize("w,h,n", [(144, 1, 2), (144, 15, 3), (136, 16, 2), (160, 17, 2), (130, 31, 1), (16384, 18, 1), (8200, 20, 1)])
+def test_extreme_geometries(hw, w, h, n):
+    """Smallest legal width, single-line and single-block-row pictures (R = 1), odd heights, very wide rows."""
+    for case in ("fgs_afgs1_test1.cfg|d10|420|g100", "fgs_sei.cfg|d10|420|g100", "fgs_sei_ff_test4.cfg|d10|444|g150"):
+        meta = G.cases[case]
+        frames = synth_frames(n, w, h, meta["fmt"], meta["depth"], seed=h)
+        o = Oracle(); program_case(o, G, case)
+        exp = o.add_grain_frames(frames, n, w, h, 0)
+        for mode in (0, 1, 2):
+            hw.reset(); program_case(hw, G, case)
+            hw.force_general_kernel(mode)
+            try:
+                got = run_device(hw, frames, n, w, h, 0, meta["depth"])
+            finally:
+                hw.force_general_kernel(0)
+            assert np.array_equal(got, exp), (case, w, h, mode, first_mismatch(got, exp, w, h, meta["fmt"], n))
+            assert hw.get_lfsr() == o.get_lfsr()
+
+
+def test_empty_batch_is_a_no_op(hw):
+    import torch
+    hw.reset(); program_case(hw, G, "fgs_afgs1_test1.cfg|d10|420|g100")
+    regs = hw.get_lfsr()
+    buf = torch.zeros(16, dtype=torch.int16, device="cuda")
+    hw.add_grain_frames_device(buf, buf, 0, 256, 144, 0)
+    hw.add_grain_frames_host(np.zeros(16, np.uint16), np.zeros(16, np.uint16), 0, 256, 144, 0)
+    assert hw.get_lfsr() == regs
+
+
 def test_launch_accounting(hw):
     hw.reset(); program_case(hw, G, "fgs_afgs1_test1.cfg|d10|420|g100")
     before = hw.launch_count()

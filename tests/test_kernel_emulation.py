@@ -93,3 +93,17 @@ def test_fast_path_garbage_samples_and_minus_128(emu):
     frames = synth_frames(n, w, h, "420", 10, seed=2)
     got, mask = run_emu(emu, o, frames, n, w, h, 0)
     assert mask == 5 and np.array_equal(got, o.add_grain_frames(frames, n, w, h, 0))
+
+
+@pytest.mark.parametrize("w,h,n", [(144, 1, 2), (144, 15, 3), (136, 16, 2), (160, 17, 2), (130, 31, 1), (16384, 18, 1), (8200, 20, 1)])
+def test_extreme_geometries(emu, w, h, n):
+    """Smallest legal width (> 128, vfgs_hw.c:168), pictures of a single line / a single block-row (R = 1:
+    the LFSR does not advance between frames), odd heights, and the widest rows the oracle supports."""
+    for case in ("fgs_afgs1_test1.cfg|d10|420|g100", "fgs_sei.cfg|d10|420|g100", "fgs_sei_ff_test4.cfg|d10|444|g150"):
+        meta = G.cases[case]
+        o = Oracle(); program_case(o, G, case)
+        frames = synth_frames(n, w, h, meta["fmt"], meta["depth"], seed=h)
+        runs = [(mode, run_emu(emu, o, frames, n, w, h, 0, mode=mode)) for mode in (0, 1, 2)]
+        want = o.add_grain_frames(frames, n, w, h, 0)
+        for mode, (got, _) in runs:
+            assert np.array_equal(got, want), (case, w, h, mode, first_mismatch(got, want, w, h, meta["fmt"], n))

@@ -36,6 +36,15 @@ def test_library_exports_every_declared_symbol(hw_lib):
     assert set(declared_functions()) <= exported
 
 
+def test_library_exports_the_yuv_layer(hw_lib):
+    """include/yuv.h: the reference's seven yuv.h entry points (src/yuv.h:60-66), batched implementation."""
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "yuv.h")).read(), flags=re.S)
+    names = sorted(set(re.findall(r"\b(yuv_[a-z0-9_]+)\s*\(", text)))
+    assert names == ["yuv_alloc", "yuv_free", "yuv_pad", "yuv_read", "yuv_skip", "yuv_to_8bit", "yuv_write"]
+    for n in names:
+        assert hasattr(hw_lib.L, n), n
+
+
 def test_library_carries_sm100a_code_only():
     out = subprocess.run(["cuobjdump", "-lelf", api.LIB_PATH], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_\d+a?", out))

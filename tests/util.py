@@ -9,54 +9,7 @@ import numpy as np
 
 from oracle.pyoracle import Oracle, program_hw_from_state, synth_frames  # noqa: F401
 
-GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden.npz")
-
-
-class Golden:
-    def __init__(self, path=GOLDEN):
-        z = np.load(path)
-        self.arrays = {k: z[k] for k in z.files}
-        meta = json.loads(bytes(self.arrays.pop("__index__")).decode())
-        self.cases, self.kat, self.seed = meta["cases"], meta["kat"], meta["seed"]
-
-    def runnable(self):
-        return [c for c, m in self.cases.items() if m.get("load_rc") == 0 and "outputs" in m]
-
-    def state(self, case: str) -> dict:
-        """Full hw state dict (pattern[2][9][64][64], slut, plut, scalars, lfsr) of a case."""
-        pat = np.zeros((2, 9, 64, 64), dtype=np.int8)
-        luma, chroma = self.arrays[case + "/luma"], self.arrays[case + "/chroma"]
-        pat[0, :luma.shape[0]] = luma
-        pat[1, :chroma.shape[0]] = chroma
-        return {"pattern": pat, "slut": self.arrays[case + "/slut"], "plut": self.arrays[case + "/plut"],
-                "scalars": self.arrays[case + "/scalars"], "lfsr": self.arrays[case + "/lfsr"]}
-
-    def struct(self, case: str) -> bytes:
-        return self.arrays[case + "/struct"].tobytes()
-
-
-def load_golden() -> Golden:
-    return Golden()
-
-
-def sha(a: np.ndarray) -> str:
-    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
-
-
-def parse_output_key(key: str):
-    """'256x152x3|s11|o8' -> (w, h, n, input seed, out depth)."""
-    dims, s, o = key.split("|")
-    w, h, n = (int(v) for v in dims.split("x"))
-    return w, h, n, int(s[1:]), int(o[1:])
-
-
-def program_case(hw, golden: Golden, case: str) -> dict:
-    """Reset-free programming of any vfgs_hw.h-shaped object from a golden case; the LFSR registers
-    are set raw so that the default (odd) register value 0xdeadbeef is reproducible too."""
-    st = golden.state(case)
-    program_hw_from_state(hw, st)
-    hw.set_lfsr([int(v) for v in st["lfsr"]])
-    return st
+from tests.fixtures import GOLDEN, Golden, load_golden, parse_output_key, program_case, sha  # noqa: E402,F401
 
 
 def states_equal(a: dict, b: dict, nslot=None) -> list:

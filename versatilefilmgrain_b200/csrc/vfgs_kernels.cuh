@@ -72,8 +72,16 @@ lfsr_states_kernel(uint32_t epoch_state, const uint32_t* __restrict__ pow2, uint
 	unsigned long long t = ((frame0 + (unsigned long long)f) * (unsigned long long)(R - 1) + (unsigned long long)r) *
 	                       (unsigned long long)nb;
 	uint32_t s = epoch_state;
-	for (int k = 0; t; k++, t >>= 1)
-		if (t & 1ull) s = __ballot_sync(0xffffffffu, __popc(pow2[k * 32 + lane] & s) & 1);
+	// matrix rows are fetched eight powers at a time, independently of the state, so the dependent
+	// chain is only AND + POPC + ballot per set bit of t
+	for (int k0 = 0; k0 < kJumpBits && (t >> k0) != 0; k0 += 8) {
+		uint32_t rows[8];
+#pragma unroll
+		for (int j = 0; j < 8; j++) rows[j] = pow2[(k0 + j) * 32 + lane];
+#pragma unroll
+		for (int j = 0; j < 8; j++)
+			if ((t >> (k0 + j)) & 1ull) s = __ballot_sync(0xffffffffu, __popc(rows[j] & s) & 1);
+	}
 	const uint32_t step32 = pow2[5 * 32 + lane];
 	uint32_t* dst = states + (size_t)warp * spitch;
 	if (lane == 0) { dst[0] = 0; dst[nb + 1] = 0; }

@@ -100,8 +100,7 @@ int vfgs_b200_kernel_time(double* total_ms, uint64_t* launches);
 
 /* Test aid: kernel selection. 0 = automatic (fast kernel for single-pattern components, gather kernel
  * for sample-adaptive ones, general kernel for ragged/unaligned layouts), 1 = general kernel for
- * everything, 2 = gather kernel wherever it can run. All three are CUDA paths. Bits 8.. of `mode`, when
- * non-zero, fix the number of block-rows a fast-kernel warp-task walks (default: chosen per batch). */
+ * everything, 2 = gather kernel wherever it can run. All three are CUDA paths. */
 void vfgs_b200_force_general_kernel(int mode);
 
 /* Frame pipeline behind include/yuv.h: out[0] = frames processed, out[1] = batches flushed. */

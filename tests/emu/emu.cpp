@@ -40,8 +40,8 @@ void run_gather(const FgsParams& p, const uint8_t* luts, const uint8_t* img)
 extern "C" int emu_state_size(void) { return (int)sizeof(StateDump); }
 
 // Packed planar frames, whole frames, like vfgs_b200_add_grain_frames_device.
-// mode & 3: 0 automatic kernel choice, 1 general task code everywhere, 2 gather task code wherever it can
-// run (plan_launches); mode >> 8: block-rows per fast-kernel task (0 = automatic). Returns a bit mask: 1 = fast, 2 = general, 4 = gather task code ran.
+// mode: 0 automatic kernel choice, 1 general task code everywhere, 2 gather task code wherever it can
+// run (plan_launches). Returns a bit mask: 1 = fast, 2 = general, 4 = gather task code ran.
 extern "C" int emu_add_grain_frames(const void* state, const void* in, void* out, int nframes, int width,
                                     int height, int out_depth, int first_frame_index, int mode)
 {
@@ -109,7 +109,7 @@ extern "C" int emu_add_grain_frames(const void* state, const void* in, void* out
 	finish_tasks(p);
 
 	LaunchPlan lp;
-	plan_launches(p, bi, mode & 3, in == out, 227 * 1024, 148 * 32 * 6, mode >> 8, lp);
+	plan_launches(p, bi, mode, in == out, 227 * 1024, lp);
 	{ // window offsets of every block (the second table lfsr_states_kernel writes), in the serving kernel's format
 		const WoffParams wp = make_woff_params(p, lp.kind);
 		for (size_t i = 0; i < states.size(); i++)

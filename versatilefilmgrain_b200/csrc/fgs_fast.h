@@ -274,29 +274,28 @@ VFGS_HD uint32_t window_offset(int c, uint32_t state, const int off[2], int stri
 constexpr int kFastLB = 4; // lines in flight per lane
 
 template <bool IN16, bool OUT8, int NSH>
-VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, smem_addr_t img, int f, int c, int r0, int r1, int k0, int lane)
+VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, smem_addr_t img, const TaskGeom& t, int k0, int lane)
 {
+	const int c = t.c;
 	const Plane& pl = p.comp[c];
 	const int ysh = (c && p.suby > 1) ? 1 : 0;
 	constexpr int n = 1 << NSH;
-	if (k0 >= pl.width) return;
 
-	// component lines of block-rows [r0, r1) (whole block-rows only: the host sends partial line ranges
-	// to the general kernel); they are contiguous in memory, so the chunk is one stream of lines
-	const int lps = 16 >> ysh; // lines per block-row
-	const int cl0 = r0 * lps;
-	int cl1 = r1 * lps;
+	// component lines of this stripe (whole stripes only: the host sends partial line ranges to
+	// the general kernel)
+	const int cl0 = (t.r * 16) >> ysh;
+	int cl1 = cl0 + (16 >> ysh);
 	if (cl1 > pl.lines) cl1 = pl.lines;
 	const int nl = cl1 - cl0;
 	if (nl <= 0) return;
 
 	constexpr int IB = IN16 ? 2 : 1, OB = (IN16 && !OUT8) ? 2 : 1;
 	const long long in_pitch = pl.in_row_bytes, out_pitch = pl.out_row_bytes;
-	const uint8_t* src = pl.in + (long long)f * p.in_frame_bytes + (long long)cl0 * in_pitch + (long long)k0 * IB;
-	uint8_t* dst = pl.out + (long long)f * p.out_frame_bytes + (long long)cl0 * out_pitch + (long long)k0 * OB;
+	const uint8_t* src = pl.in + (long long)t.f * p.in_frame_bytes + (long long)cl0 * in_pitch + (long long)k0 * IB;
+	uint8_t* dst = pl.out + (long long)t.f * p.out_frame_bytes + (long long)cl0 * out_pitch + (long long)k0 * OB;
 
-	// The first kFastLB lines are requested before anything else: the set-up below runs while they
-	// are in flight. A chunk shorter than kFastLB lines re-reads its last line.
+	// The first kFastLB lines are requested before anything else: the block decode below runs
+	// while they are in flight. A stripe shorter than kFastLB lines re-reads its last line.
 	uint32_t raw[kFastLB][4];
 #pragma unroll
 	for (int q = 0; q < kFastLB; q++) {
@@ -315,35 +314,25 @@ VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, smem_addr_t img
 	L.pow16 = p.pow16;
 	L.lo2 = (uint32_t)p.lo[c] * 0x00010001u; L.hi2 = (uint32_t)p.hi[c] * 0x00010001u;
 
-	// pattern windows of this block and its neighbours (precomputed per block by lfsr_states_kernel)
-	const long long wpitch = (long long)p.spitch * 4;
-	const uint16_t* w_row = p.woffs + (((long long)f * p.stream_rows + (r0 - p.stream_row0)) * p.spitch + 1 + b) * 4 + c;
-	L.own = img + (smem_addr_t)(w_row[0] + i0);
+	const int srow = t.r - p.stream_row0;
+	const uint16_t* w_cur = p.woffs + (((long long)t.f * p.stream_rows + srow) * p.spitch + 1 + b) * 4 + c;
+	L.own = img + (smem_addr_t)(w_cur[0] + i0);
 	L.lh = L.rh = L.own;
-	if (L.has_left) L.lh = img + (smem_addr_t)(w_row[-4] + n - 1);
-	if (L.has_right) L.rh = img + (smem_addr_t)w_row[4];
+	if (L.has_left) L.lh = img + (smem_addr_t)(w_cur[-4] + n - 1);
+	if (L.has_right) L.rh = img + (smem_addr_t)w_cur[4];
 
-	// the first lines of a block-row overlap the row above (never in the first row of a picture, y <= 15)
+	// the first lines of a stripe overlap the block-row above (never in the first stripe, y <= 15)
 	FastUp U;
 	U.own = U.lh = U.rh = L.own;
-	bool ovl = r0 > 0;
+	bool ovl = t.r > 0;
 	if (ovl) {
-		const uint16_t* w_up = w_row - wpitch;
+		const uint16_t* w_up = w_cur - p.spitch * 4;
 		U.own = img + (smem_addr_t)(w_up[0] + i0);
 		if (L.has_left) U.lh = img + (smem_addr_t)(w_up[-4] + n - 1);
 		if (L.has_right) U.rh = img + (smem_addr_t)w_up[4];
 	}
-	// windows of the next block-row, fetched one row ahead of their use
-	int rows_left = r1 - r0 - 1;
-	uint32_t n_own = 0, n_lh = 0, n_rh = 0;
-	w_row += wpitch;
-	if (rows_left > 0) {
-		n_own = w_row[0];
-		if (L.has_left) n_lh = w_row[-4];
-		if (L.has_right) n_rh = w_row[4];
-	}
 
-	int rc = 0, in_row = 0;
+	int rc = 0;
 	const uint8_t* nxt = src + kFastLB * in_pitch; // line whose load refills the slot just consumed
 #pragma unroll 1
 	for (int base = 0; base < nl; base += kFastLB) {
@@ -365,45 +354,32 @@ VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, smem_addr_t img
 			rc += L.stride; nxt += in_pitch; dst += out_pitch;
 		}
 		ovl = false;
-		in_row += kFastLB;
-		if (in_row == lps && rows_left > 0) {
-			// next block-row of the column: its windows were fetched a row ago, this row's become the upper ones
-			U.own = L.own; U.lh = L.lh; U.rh = L.rh;
-			L.own = img + (smem_addr_t)(n_own + i0);
-			L.lh = L.rh = L.own;
-			if (L.has_left) L.lh = img + (smem_addr_t)(n_lh + n - 1);
-			if (L.has_right) L.rh = img + (smem_addr_t)n_rh;
-			rc = 0; in_row = 0; ovl = true;
-			rows_left--;
-			w_row += wpitch;
-			if (rows_left > 0) {
-				n_own = w_row[0];
-				if (L.has_left) n_lh = w_row[-4];
-				if (L.has_right) n_rh = w_row[4];
-			}
-		}
 	}
 }
 
-// Fast-kernel task numbering (FgsParams::fstripes ...): per frame the components one after the other;
-// inside a component chunk-major, then the 256-sample columns. Dispatch on the component's block size
-// (16 samples: luma and non-subsampled chroma; 8: chroma subsampled horizontally).
+// Dispatch on the component's block size (16 samples: luma and non-subsampled chroma; 8: chroma
+// subsampled horizontally).
+// Fast-kernel task numbering: per frame the components one after the other; inside a component the
+// stripes' rows are one flat run of lane units (8 samples), 32 consecutive units per warp-task, so only
+// the very last task of a component can have idle lanes (a row need not be a multiple of 256 samples).
 template <bool IN16, bool OUT8>
 VFGS_HD void process_task_fast(const FgsParams& p, smem_addr_t lut, smem_addr_t img, uint32_t task, int lane)
 {
-	const int f = (int)fastdiv(task, p.div_ftasks);
-	uint32_t q = task - (uint32_t)f * (uint32_t)p.ftasks_per_frame;
-	int c = 0;
-	if (q >= (uint32_t)p.ftasks[0]) { q -= (uint32_t)p.ftasks[0]; c = 1; }
-	if (c == 1 && q >= (uint32_t)p.ftasks[1]) { q -= (uint32_t)p.ftasks[1]; c = 2; }
-	const uint32_t chunk = fastdiv(q, p.div_fcols[c]);
-	const uint32_t col = q - chunk * (uint32_t)p.fcols[c];
-	const int r0 = p.row_begin + (int)chunk * p.fstripes;
-	int r1 = r0 + p.fstripes;
-	if (r1 > p.row_begin + p.rows) r1 = p.row_begin + p.rows;
-	const int k0 = (int)col * kSegSamples + lane * kSamplesPerLane;
-	if (c && p.subx > 1) fast_task_body<IN16, OUT8, 3>(p, lut, img, f, c, r0, r1, k0, lane);
-	else fast_task_body<IN16, OUT8, 4>(p, lut, img, f, c, r0, r1, k0, lane);
+	TaskGeom t;
+	t.f = (int)fastdiv(task, p.div_ftasks);
+	uint32_t q = task - (uint32_t)t.f * (uint32_t)p.ftasks_per_frame;
+	t.c = 0;
+	if (q >= (uint32_t)p.ftasks[0]) { q -= (uint32_t)p.ftasks[0]; t.c = 1; }
+	if (t.c == 1 && q >= (uint32_t)p.ftasks[1]) { q -= (uint32_t)p.ftasks[1]; t.c = 2; }
+	const uint32_t unit = q * 32u + (uint32_t)lane;
+	const uint32_t upr = (uint32_t)p.funits_per_row[t.c];
+	if (unit >= upr * (uint32_t)p.rows) return;
+	const uint32_t row = fastdiv(unit, p.div_funits[t.c]);
+	t.r = p.row_begin + (int)row;
+	t.seg = 0;
+	const int k0 = (int)(unit - row * upr) * kSamplesPerLane;
+	if (t.c && p.subx > 1) fast_task_body<IN16, OUT8, 3>(p, lut, img, t, k0, lane);
+	else fast_task_body<IN16, OUT8, 4>(p, lut, img, t, k0, lane);
 }
 
 } // namespace vfgs

@@ -67,7 +67,6 @@ std::vector<uint8_t> g_blob;
 TableInfo g_bi;
 std::vector<uint8_t> g_fblob;
 uint64_t g_launches = 0;
-int g_fast_stripes = 0; // test hook: chunk height of the fast kernel (0 = automatic)
 int g_kernel_mode = 0; // test hook: 0 auto, 1 general kernel everywhere, 2 gather kernel wherever it can run
 char g_err[512] = "";
 const JumpTable& jump_table()
@@ -329,8 +328,7 @@ int run_frames_device(const vfgs_b200_planes& in, const vfgs_b200_planes& out, i
 	// every component goes to the cheapest kernel that can serve it (plan_launches)
 	g_ctx.last_launch[4] = 0;
 	LaunchPlan lp;
-	// chunk height of the fast kernel: every resident warp (32 per SM) should still get ~6 tasks
-	plan_launches(p, g_bi, g_kernel_mode, in.y == out.y, g_ctx.max_smem_optin - 1024, (long long)g_ctx.sm_count * 32 * 6, g_fast_stripes, lp);
+	plan_launches(p, g_bi, g_kernel_mode, in.y == out.y, g_ctx.max_smem_optin - 1024, lp);
 	if (int rc = launch_streams(epoch, d_streams, d_woffs, make_woff_params(p, lp.kind), n, g, frame0, stream)) return rc;
 	if (lp.any_fast)
 		if (int rc = launch_apply(lp.fast, stream, kFast)) return rc;
@@ -670,7 +668,7 @@ void vfgs_b200_host_free(void* p)
 
 uint64_t vfgs_b200_launch_count(void) { return g_launches; }
 
-void vfgs_b200_force_general_kernel(int mode) { g_kernel_mode = mode & 3; g_fast_stripes = mode >> 8; }
+void vfgs_b200_force_general_kernel(int mode) { g_kernel_mode = mode; }
 
 int vfgs_b200_kernel_timing(int enable)
 {

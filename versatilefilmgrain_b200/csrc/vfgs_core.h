@@ -167,11 +167,10 @@ struct FgsParams {
 	int uniform_pi[3];      // pattern slot when the pattern LUT selects a single slot, else -1
 	int nseg[3], tasks_per_stripe;
 	FastDiv div_tps, div_rows; // reciprocals of tasks_per_stripe and rows
-	// fast kernel task numbering: a warp-task is a column of 256 samples (32 lanes x 8) walked down
-	// fstripes consecutive block-rows ("chunk"), so the per-lane set-up is paid once per chunk and the
-	// current block-row's windows become the next one's upper windows. Per frame: component, chunk, column.
-	int fstripes, fchunks, fcols[3], ftasks[3], ftasks_per_frame;
-	FastDiv div_fcols[3], div_ftasks;
+	// fast kernel task numbering: a component's stripes are one flat run of 8-sample lane units
+	// (units_per_row * rows of them per frame), cut into warp-tasks of 32 units regardless of row ends
+	int funits_per_row[3], ftasks[3], ftasks_per_frame;
+	FastDiv div_funits[3], div_ftasks;
 	// table image ("blob") copied to shared memory by every CTA
 	const uint8_t* blob;
 	int blob_bytes;

@@ -148,9 +148,7 @@ inline void finish_tasks(FgsParams& p)
 //   gather  several pattern slots (or a -128 byte), same alignment conditions, out of place (fgs_gather.h)
 //   general everything else: ragged widths, unaligned rows                               (fgs_task.h)
 // mode: 0 = as above, 1 = general kernel for everything, 2 = gather kernel wherever it can run
-// (1 and 2 exist for the tests). smem_limit: opt-in shared memory per block of the device. target_tasks: how
-// many fast-kernel warp-tasks a launch should at least have; stripes_per_task > 0 overrides the resulting
-// chunk height (tests).
+// (1 and 2 exist for the tests). smem_limit: opt-in shared memory per block of the device.
 struct LaunchPlan {
 	FgsParams fast, gather, general;
 	bool any_fast, any_gather, any_general;
@@ -158,8 +156,7 @@ struct LaunchPlan {
 	int gather_smem; // dynamic shared memory of the gather launch
 };
 
-inline void plan_launches(const FgsParams& p, const TableInfo& bi, int mode, bool in_place, int smem_limit, long long target_tasks,
-                          int stripes_per_task, LaunchPlan& lp)
+inline void plan_launches(const FgsParams& p, const TableInfo& bi, int mode, bool in_place, int smem_limit, LaunchPlan& lp)
 {
 	lp.fast = lp.gather = lp.general = p;
 	lp.any_fast = lp.any_gather = lp.any_general = false;
@@ -187,24 +184,15 @@ inline void plan_launches(const FgsParams& p, const TableInfo& bi, int mode, boo
 		if (kind[c] != 2) lp.general.nseg[c] = 0;
 		(kind[c] == 0 ? lp.any_fast : kind[c] == 1 ? lp.any_gather : lp.any_general) = true;
 	}
-	// the fast kernel walks columns of 256 samples down chunks of block-rows (process_task_fast): chunks
-	// as tall as the batch allows while leaving every resident warp several tasks
+	// the fast kernel numbers its tasks over flat runs of lane units (process_task_fast)
 	{
 		FgsParams& f = lp.fast;
-		int cols = 0;
-		for (int c = 0; c < 3; c++) {
-			f.fcols[c] = kind[c] == 0 ? (f.comp[c].width + kSegSamples - 1) / kSegSamples : 0;
-			cols += f.fcols[c];
-		}
-		long long s = stripes_per_task;
-		if (s <= 0) s = ((long long)f.nframes * f.rows * cols) / (target_tasks > 0 ? target_tasks : 1);
-		f.fstripes = (int)(s < 1 ? 1 : s > 16 ? 16 : s);
-		f.fchunks = (f.rows + f.fstripes - 1) / f.fstripes;
 		f.ftasks_per_frame = 0;
 		for (int c = 0; c < 3; c++) {
-			f.ftasks[c] = f.fcols[c] * f.fchunks;
+			f.funits_per_row[c] = kind[c] == 0 ? f.comp[c].width / kSamplesPerLane : 0;
+			f.ftasks[c] = (f.funits_per_row[c] * f.rows + 31) / 32;
 			f.ftasks_per_frame += f.ftasks[c];
-			f.div_fcols[c] = make_fastdiv((uint32_t)(f.fcols[c] > 0 ? f.fcols[c] : 1));
+			f.div_funits[c] = make_fastdiv((uint32_t)(f.funits_per_row[c] > 0 ? f.funits_per_row[c] : 1));
 		}
 		f.div_ftasks = make_fastdiv((uint32_t)(f.ftasks_per_frame > 0 ? f.ftasks_per_frame : 1));
 	}

@@ -127,7 +127,7 @@ inline int lds_u8(smem_addr_t a) { return (int)*(const uint8_t*)a; }
 VFGS_HD void ld_global_16_if(const uint8_t* p, uint32_t r[4], bool pred)
 {
 #if defined(__CUDA_ARCH__)
-	asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];\n\t}"
+	asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q ld.global" VFGS_LD_OP ".v4.u32 {%0,%1,%2,%3}, [%4];\n\t}"
 	             : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]) : "l"(p), "r"((uint32_t)pred));
 #else
 	if (pred) memcpy(r, p, 16);
@@ -136,7 +136,7 @@ VFGS_HD void ld_global_16_if(const uint8_t* p, uint32_t r[4], bool pred)
 VFGS_HD void ld_global_8_if(const uint8_t* p, uint32_t r[2], bool pred)
 {
 #if defined(__CUDA_ARCH__)
-	asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q ld.global.L1::no_allocate.v2.u32 {%0,%1}, [%2];\n\t}"
+	asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q ld.global" VFGS_LD_OP ".v2.u32 {%0,%1}, [%2];\n\t}"
 	             : "+r"(r[0]), "+r"(r[1]) : "l"(p), "r"((uint32_t)pred));
 #else
 	if (pred) memcpy(r, p, 8);

@@ -18,10 +18,18 @@
 namespace vfgs {
 
 // ---- global memory access -------------------------------------------------------------------
+// Samples are streamed: read once, written once. Cache operators of the 128-bit loads / stores
+// (overridable at build time for experiments: -DVFGS_LD_OP='".cs"').
+#ifndef VFGS_LD_OP
+#define VFGS_LD_OP ".L1::no_allocate"
+#endif
+#ifndef VFGS_ST_OP
+#define VFGS_ST_OP ".L1::no_allocate"
+#endif
 VFGS_HD void ld_global_16(const uint8_t* p, uint32_t r[4])
 {
 #if defined(__CUDA_ARCH__)
-	asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+	asm volatile("ld.global" VFGS_LD_OP ".v4.u32 {%0,%1,%2,%3}, [%4];"
 	             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "l"(p));
 #else
 	memcpy(r, p, 16);
@@ -30,7 +38,7 @@ VFGS_HD void ld_global_16(const uint8_t* p, uint32_t r[4])
 VFGS_HD void ld_global_8(const uint8_t* p, uint32_t r[2])
 {
 #if defined(__CUDA_ARCH__)
-	asm volatile("ld.global.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "l"(p));
+	asm volatile("ld.global" VFGS_LD_OP ".v2.u32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "l"(p));
 #else
 	memcpy(r, p, 8);
 #endif
@@ -38,7 +46,7 @@ VFGS_HD void ld_global_8(const uint8_t* p, uint32_t r[2])
 VFGS_HD void st_global_16(uint8_t* p, const uint32_t r[4])
 {
 #if defined(__CUDA_ARCH__)
-	asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+	asm volatile("st.global" VFGS_ST_OP ".v4.u32 [%0], {%1,%2,%3,%4};"
 	             :: "l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
 #else
 	memcpy(p, r, 16);
@@ -47,7 +55,7 @@ VFGS_HD void st_global_16(uint8_t* p, const uint32_t r[4])
 VFGS_HD void st_global_8(uint8_t* p, const uint32_t r[2])
 {
 #if defined(__CUDA_ARCH__)
-	asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" :: "l"(p), "r"(r[0]), "r"(r[1]) : "memory");
+	asm volatile("st.global" VFGS_ST_OP ".v2.u32 [%0], {%1,%2};" :: "l"(p), "r"(r[0]), "r"(r[1]) : "memory");
 #else
 	memcpy(p, r, 8);
 #endif

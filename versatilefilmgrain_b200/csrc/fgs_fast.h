@@ -123,6 +123,34 @@ inline int lds_s8(smem_addr_t a) { return (int)*(const int8_t*)a; }
 inline int lds_u8(smem_addr_t a) { return (int)*(const uint8_t*)a; }
 #endif
 
+// Measured on B200 (scripts/variant_sweep.sh): with 16-bit output the fast kernel is HBM-bound and runs
+// ~2 % faster when the sample loads allocate in L1 (whole 128-byte lines are brought in ahead of the
+// neighbouring lanes' requests); with 8-bit output it is issue-bound and the streaming operator is ahead.
+template <bool L1_ALLOCATE>
+VFGS_HD void ld_samples_16(const uint8_t* p, uint32_t r[4])
+{
+#if defined(__CUDA_ARCH__)
+	if (L1_ALLOCATE) asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "l"(p));
+	else ld_global_16(p, r);
+#else
+	memcpy(r, p, 16);
+#endif
+}
+template <bool L1_ALLOCATE>
+VFGS_HD void ld_samples_16_if(const uint8_t* p, uint32_t r[4], bool pred)
+{
+#if defined(__CUDA_ARCH__)
+	if (L1_ALLOCATE)
+		asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q ld.global.v4.u32 {%0,%1,%2,%3}, [%4];\n\t}"
+		             : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]) : "l"(p), "r"((uint32_t)pred));
+	else
+		asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q ld.global" VFGS_LD_OP ".v4.u32 {%0,%1,%2,%3}, [%4];\n\t}"
+		             : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]) : "l"(p), "r"((uint32_t)pred));
+#else
+	if (pred) memcpy(r, p, 16);
+#endif
+}
+
 // global load that only happens when pred is set; the destination keeps its value otherwise
 VFGS_HD void ld_global_16_if(const uint8_t* p, uint32_t r[4], bool pred)
 {
@@ -271,7 +299,10 @@ VFGS_HD uint32_t window_offset(int c, uint32_t state, const int off[2], int stri
 	return (uint32_t)(off[o.sign < 0 ? 1 : 0] + o.oy * stride + o.ox);
 }
 
-constexpr int kFastLB = 4; // lines in flight per lane
+#ifndef VFGS_FAST_LB
+#define VFGS_FAST_LB 4
+#endif
+constexpr int kFastLB = VFGS_FAST_LB; // lines in flight per lane (build-time knob for experiments)
 
 template <bool IN16, bool OUT8, int NSH>
 VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, smem_addr_t img, const TaskGeom& t, int k0, int lane)
@@ -300,7 +331,7 @@ VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, smem_addr_t img
 #pragma unroll
 	for (int q = 0; q < kFastLB; q++) {
 		const int qq = q < nl ? q : nl - 1;
-		if (IN16) ld_global_16(src + qq * in_pitch, raw[q]);
+		if (IN16) ld_samples_16<!OUT8>(src + qq * in_pitch, raw[q]);
 		else ld_global_8(src + qq * in_pitch, raw[q]);
 	}
 
@@ -345,7 +376,7 @@ VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, smem_addr_t img
 			if (q == 1 && ovl && !ysh) { w_cur = 24; w_up = 12; ru = 17 * L.stride; }
 			fast_line<IN16, OUT8, NSH>(L, rc, w_cur, w_up, U, ru, raw[q], w);
 			// this slot's registers are free again: request the line kFastLB further down
-			if (IN16) ld_global_16_if(nxt, raw[q], line + kFastLB < nl);
+			if (IN16) ld_samples_16_if<!OUT8>(nxt, raw[q], line + kFastLB < nl);
 			else ld_global_8_if(nxt, raw[q], line + kFastLB < nl);
 			if (line < nl) {
 				if (OB == 2) st_global_16(dst, w);

@@ -126,11 +126,15 @@ fgs_apply_kernel(const __grid_constant__ FgsParams p)
 // Fast path: single-pattern components, aligned rows (fgs_fast.h). 512-thread persistent CTAs, two
 // per SM; shared memory = per-lane replicated scale LUT (32 KB, expanded here from the 1 KB compact
 // LUT) + the +/- pattern copies, brought in by one bulk async copy.
-constexpr int kFastThreads = 512;
+#ifndef VFGS_FAST_THREADS
+#define VFGS_FAST_THREADS 512
+#define VFGS_FAST_CTAS 2
+#endif
+constexpr int kFastThreads = VFGS_FAST_THREADS; // build-time knobs for experiments
 constexpr int kFastWarps = kFastThreads / 32;
 
 template <bool IN16, bool OUT8>
-__global__ void __launch_bounds__(kFastThreads, 2)
+__global__ void __launch_bounds__(kFastThreads, VFGS_FAST_CTAS)
 fgs_apply_fast_kernel(const __grid_constant__ FgsParams p)
 {
 	extern __shared__ __align__(128) uint8_t smem[];

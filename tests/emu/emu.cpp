@@ -71,11 +71,11 @@ extern "C" int emu_add_grain_frames(const void* state, const void* in, void* out
 	std::vector<uint32_t> tab_store((blob.size() + 64) / 4);
 	uint8_t* tab = (uint8_t*)tab_store.data();
 	memcpy(tab, blob.data(), blob.size());
-	std::vector<uint8_t> smem_store((size_t)kLutAlign + kLutBytes + fblob.size() + 64);
+	std::vector<uint8_t> smem_store((size_t)kLutAlign + 3 * kLutBytes + fblob.size() + 64);
 	uint8_t* lut_ptr = (uint8_t*)(((uintptr_t)smem_store.data() + kLutAlign - 1) & ~(uintptr_t)(kLutAlign - 1));
-	uint8_t* img_ptr = lut_ptr + kLutBytes;
+	uint8_t* img_ptr = lut_ptr + 3 * kLutBytes;
 	memcpy(img_ptr, fblob.data(), fblob.size());
-	for (int i = 0; i < 256 * 32; i++) ((uint32_t*)lut_ptr)[i] = ((const uint32_t*)img_ptr)[i >> 5];
+	expand_fast_luts((uint32_t*)lut_ptr, (const uint32_t*)img_ptr, (uint32_t)(1 << (16 - h.scale_shift)), 0, 1);
 
 	// per-block LFSR registers (what lfsr_states_kernel produces)
 	std::vector<uint32_t> states((size_t)nframes * R * spitch, 0);

@@ -17,6 +17,7 @@
 //     instructions (VIADDMNMX / VIMNMX .S16x2); 10-bit samples stay packed in their load words.
 // Host-compilable like fgs_task.h (tests/emu) -- the helpers below emulate the few PTX instructions.
 #pragma once
+#include <type_traits>
 #include "fgs_task.h"
 
 namespace vfgs {
@@ -101,13 +102,24 @@ VFGS_HD uint32_t mulhi_u32(uint32_t a, uint32_t b)
 }
 
 // ---- shared-memory image of the fast path --------------------------------------------------
-//   lut   uint32 lut[256][32], per-lane replicated scale LUT (built by the CTA), placed on a 32 KB
-//         boundary of the shared window so that "lane column | index bits" is a plain OR
+//   lut   uint32 lut[3][256][32]: per component a per-lane replicated LUT of scale << (16 - scale_shift)
+//         (built by the CTA from the compact LUT), each table on a 32 KB boundary of the shared window so
+//         that "lane column | index bits" is a plain OR
 //   img   copy of the global image: uint32 compact_lut[256], then for each component its pattern slot
 //         twice (+ and -), rows packed to fpat_stride bytes; fpat_off is relative to img
 // Addresses are absolute: 32-bit shared-window addresses on the device, pointers in the host build.
 constexpr int kLutBytes = 256 * 32 * 4;
 constexpr int kLutAlign = 32768;
+
+// lut[c][i][lane] = sLUT[c][i] << (16 - shift) from compact[i] = sLUT[Y][i] | sLUT[U][i] << 8 | sLUT[V][i] << 16;
+// thread `tid` of `nthreads` does its share (the host build calls it with one thread).
+VFGS_HD void expand_fast_luts(uint32_t* lut, const uint32_t* compact, uint32_t pow16, int tid, int nthreads)
+{
+	for (int i = tid; i < 3 * 256 * 32; i += nthreads) {
+		const int c = i >> 13;
+		lut[i] = ((compact[(i >> 5) & 255] >> (8 * c)) & 0xffu) * pow16;
+	}
+}
 
 #if defined(__CUDA_ARCH__)
 typedef uint32_t smem_addr_t;
@@ -195,10 +207,9 @@ VFGS_HD void octet(smem_addr_t a, uint32_t& w0, uint32_t& w1)
 struct FastLane {
 	smem_addr_t own;         // the lane's octet, pattern row of line j = 0 of the current block
 	smem_addr_t lh, rh;      // halo bytes: last column of block b-1 / first column of block b+1
-	smem_addr_t lut;         // this lane's LUT column + component byte (index bits 7..14 are zero)
+	smem_addr_t lut;         // this lane's column of the component's LUT (index bits 7..14 are zero)
 	int stride;              // pattern row pitch
 	bool has_left, has_right;
-	int pow16;               // 1 << (16 - scale_shift): products land in the upper half-word
 	uint32_t lo2, hi2;       // clip range replicated in both 16-bit halves
 };
 // Same addresses for the block-row above, only alive while the overlap lines are processed.
@@ -247,17 +258,20 @@ VFGS_HD void fast_line(const FastLane& L, int rc, int w_cur, int w_up, const Fas
 	g[0] = L.has_left ? f0 : g[0];
 	g[7] = L.has_right ? f7 : g[7];
 
-	// scale * grain, rounded shift (vfgs_hw.c:263): with the grain pre-multiplied by 2^(16 - shift)
-	// the rounded quotient is exactly the upper half-word of scale * grain' + 0x8000
+	// scale * grain, rounded shift (vfgs_hw.c:263): the LUT holds scale * 2^(16 - shift), so the rounded
+	// quotient is exactly the upper half-word of lut * grain + 0x8000
 	if (IN16) {
+		// 8-bit output (yuv.c:231, (x + 2) >> 2): the + 2 rides on the rounding constant and on the clip
+		// range (FastLane::lo2/hi2 hold lo + 2, hi + 2), clip(v + d, lo, hi) + 2 == clip(v + d + 2, lo + 2, hi + 2)
+		constexpr int kRound = OUT8 ? 0x28000 : 0x8000;
 		uint32_t r[4];
 #pragma unroll
 		for (int k = 0; k < 4; k++) {
 			// LUT index = (sample >> 2) & 0xff (vfgs_hw.c:211), times the 128-byte LUT row pitch
-			const int s_lo = lds_u8(L.lut | (smem_addr_t)((raw[k] << 5) & 0x7f80u));
-			const int s_hi = lds_u8(L.lut | (smem_addr_t)(mulhi_u32(raw[k], 1u << 21) & 0x7f80u)); // raw >> 11 on the FMA pipe
-			const int a_lo = s_lo * (g[2 * k] * L.pow16) + 0x8000;
-			const int a_hi = s_hi * (g[2 * k + 1] * L.pow16) + 0x8000;
+			const int s_lo = (int)lds32(L.lut | (smem_addr_t)((raw[k] << 5) & 0x7f80u));
+			const int s_hi = (int)lds32(L.lut | (smem_addr_t)(mulhi_u32(raw[k], 1u << 21) & 0x7f80u)); // raw >> 11 on the FMA pipe
+			const int a_lo = s_lo * g[2 * k] + kRound;
+			const int a_hi = s_hi * g[2 * k + 1] + kRound;
 			const uint32_t d2 = prmt((uint32_t)a_lo, (uint32_t)a_hi, 0x7632);
 			// samples above 0x3fff clip to the ceiling whatever the grain: cap them so the signed 16-bit add cannot wrap
 			const uint32_t v2 = min_u16x2(raw[k], 0x3fff3fffu);
@@ -265,7 +279,7 @@ VFGS_HD void fast_line(const FastLane& L, int rc, int w_cur, int w_up, const Fas
 		}
 		if (OUT8) {
 #pragma unroll
-			for (int k = 0; k < 4; k++) r[k] = ((r[k] + 0x00020002u) >> 2) & 0x00ff00ffu; // yuv.c:231
+			for (int k = 0; k < 4; k++) r[k] >>= 2; // bits leaking across the half-words land in bytes 1 and 3, which are dropped
 			outw[0] = prmt(r[0], r[1], 0x6420);
 			outw[1] = prmt(r[2], r[3], 0x6420);
 		} else {
@@ -280,8 +294,8 @@ VFGS_HD void fast_line(const FastLane& L, int rc, int w_cur, int w_up, const Fas
 			const int sh = (e & 3) * 8;
 			const int v = (int)((word >> sh) & 0xff);
 			const uint32_t ibits = sh >= 7 ? (word >> (sh - 7)) & 0x7f80u : (word << (7 - sh)) & 0x7f80u; // v * 128
-			const int s = lds_u8(L.lut | (smem_addr_t)ibits);
-			int x = v + ((s * (g[e] * L.pow16) + 0x8000) >> 16);
+			const int s = (int)lds32(L.lut | (smem_addr_t)ibits);
+			int x = v + ((s * g[e] + 0x8000) >> 16);
 			x = x > hi ? hi : x;
 			o[e] = x < lo ? lo : x;
 		}
@@ -341,9 +355,9 @@ VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, smem_addr_t img
 	L.has_left = (i0 == 0) && (b > 0);
 	L.has_right = (i0 + kSamplesPerLane == n) && (b + 1 < p.nb);
 	L.stride = p.fpat_stride[c];
-	L.lut = lut + (smem_addr_t)(lane * 4 + c);
-	L.pow16 = p.pow16;
-	L.lo2 = (uint32_t)p.lo[c] * 0x00010001u; L.hi2 = (uint32_t)p.hi[c] * 0x00010001u;
+	L.lut = lut + (smem_addr_t)(c * kLutBytes + lane * 4);
+	constexpr int kOutBias = (IN16 && OUT8) ? 2 : 0; // see fast_line
+	L.lo2 = (uint32_t)(p.lo[c] + kOutBias) * 0x00010001u; L.hi2 = (uint32_t)(p.hi[c] + kOutBias) * 0x00010001u;
 
 	const int srow = t.r - p.stream_row0;
 	const uint16_t* w_cur = p.woffs + (((long long)t.f * p.stream_rows + srow) * p.spitch + 1 + b) * 4 + c;
@@ -365,27 +379,36 @@ VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, smem_addr_t img
 
 	int rc = 0;
 	const uint8_t* nxt = src + kFastLB * in_pitch; // line whose load refills the slot just consumed
+	// WHOLE: the stripe is a whole number of kFastLB-line groups (every stripe of a picture whose height is a
+	// multiple of kFastLB component lines): no per-line store predicate, one refill predicate per group.
+	auto lines = [&](auto whole_tag) {
+		constexpr bool WHOLE = decltype(whole_tag)::value;
 #pragma unroll 1
-	for (int base = 0; base < nl; base += kFastLB) {
+		for (int base = 0; base < nl; base += kFastLB) {
+			const bool more = base + kFastLB < nl;
 #pragma unroll
-		for (int q = 0; q < kFastLB; q++) {
-			const int line = base + q;
-			uint32_t w[4];
-			int w_cur = 0, w_up = 0, ru = 0;
-			if (q == 0 && ovl) { w_cur = ysh ? 20 : 12; w_up = ysh ? 20 : 24; ru = (16 >> ysh) * L.stride; }
-			if (q == 1 && ovl && !ysh) { w_cur = 24; w_up = 12; ru = 17 * L.stride; }
-			fast_line<IN16, OUT8, NSH>(L, rc, w_cur, w_up, U, ru, raw[q], w);
-			// this slot's registers are free again: request the line kFastLB further down
-			if (IN16) ld_samples_16_if<!OUT8>(nxt, raw[q], line + kFastLB < nl);
-			else ld_global_8_if(nxt, raw[q], line + kFastLB < nl);
-			if (line < nl) {
-				if (OB == 2) st_global_16(dst, w);
-				else st_global_8(dst, w);
+			for (int q = 0; q < kFastLB; q++) {
+				const int line = base + q;
+				uint32_t w[4];
+				int w_cur = 0, w_up = 0, ru = 0;
+				if (q == 0 && ovl) { w_cur = ysh ? 20 : 12; w_up = ysh ? 20 : 24; ru = (16 >> ysh) * L.stride; }
+				if (q == 1 && ovl && !ysh) { w_cur = 24; w_up = 12; ru = 17 * L.stride; }
+				fast_line<IN16, OUT8, NSH>(L, rc, w_cur, w_up, U, ru, raw[q], w);
+				// this slot's registers are free again: request the line kFastLB further down
+				const bool refill = WHOLE ? more : line + kFastLB < nl;
+				if (IN16) ld_samples_16_if<!OUT8>(nxt, raw[q], refill);
+				else ld_global_8_if(nxt, raw[q], refill);
+				if (WHOLE || line < nl) {
+					if (OB == 2) st_global_16(dst, w);
+					else st_global_8(dst, w);
+				}
+				rc += L.stride; nxt += in_pitch; dst += out_pitch;
 			}
-			rc += L.stride; nxt += in_pitch; dst += out_pitch;
+			ovl = false;
 		}
-		ovl = false;
-	}
+	};
+	if (nl % kFastLB == 0) lines(std::true_type());
+	else lines(std::false_type());
 }
 
 // Dispatch on the component's block size (16 samples: luma and non-subsampled chroma; 8: chroma

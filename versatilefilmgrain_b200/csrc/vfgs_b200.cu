@@ -171,8 +171,8 @@ int upload_blob()
 	}
 	if (int rc = grow(c.d_fblob, c.fblob_cap, (size_t)g_bi.fbytes)) return rc;
 	CUDA_TRY(cudaMemcpy(c.d_fblob, g_fblob.data(), (size_t)g_bi.fbytes, cudaMemcpyHostToDevice));
-	if (kLutAlign + kLutBytes + g_bi.fbytes > c.fast_smem_attr) {
-		const int need = kLutAlign + kLutBytes + g_bi.fbytes;
+	if (kLutAlign + 3 * kLutBytes + g_bi.fbytes > c.fast_smem_attr) {
+		const int need = kLutAlign + 3 * kLutBytes + g_bi.fbytes;
 		CUDA_TRY(cudaFuncSetAttribute(fgs_apply_fast_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
 		CUDA_TRY(cudaFuncSetAttribute(fgs_apply_fast_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
 		CUDA_TRY(cudaFuncSetAttribute(fgs_apply_fast_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
@@ -237,7 +237,7 @@ int launch_apply(const FgsParams& p, cudaStream_t stream, KernelKind kind = kGen
 	if (kind == kFast) {
 		kern = p.in_bytes == 1 ? fgs_apply_fast_kernel<false, false>
 		     : p.out_bytes == 1 ? fgs_apply_fast_kernel<true, true> : fgs_apply_fast_kernel<true, false>;
-		threads = kFastThreads; smem = kLutAlign + kLutBytes + p.fblob_bytes; // slack to place the LUT on a 32 KB boundary
+		threads = kFastThreads; smem = kLutAlign + 3 * kLutBytes + p.fblob_bytes; // slack to place the LUTs on a 32 KB boundary
 	} else if (kind == kGather) {
 		kern = p.in_bytes == 1 ? fgs_apply_gather_kernel<false, false>
 		     : p.out_bytes == 1 ? fgs_apply_gather_kernel<true, true> : fgs_apply_gather_kernel<true, false>;

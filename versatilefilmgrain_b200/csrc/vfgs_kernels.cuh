@@ -123,12 +123,13 @@ fgs_apply_kernel(const __grid_constant__ FgsParams p)
 		process_task(p, tab, (uint32_t)task, lane);
 }
 
-// Fast path: single-pattern components, aligned rows (fgs_fast.h). 512-thread persistent CTAs, two
-// per SM; shared memory = per-lane replicated scale LUT (32 KB, expanded here from the 1 KB compact
-// LUT) + the +/- pattern copies, brought in by one bulk async copy.
+// Fast path: single-pattern components, aligned rows (fgs_fast.h). One 1024-thread persistent CTA per
+// SM (measured faster than 2 x 512: one table image per SM, more of the unified array left to L1);
+// shared memory = three per-lane replicated LUTs of scale << (16 - shift) (3 x 32 KB, expanded here from
+// the 1 KB compact LUT) + the +/- pattern copies, brought in by one bulk async copy.
 #ifndef VFGS_FAST_THREADS
-#define VFGS_FAST_THREADS 512
-#define VFGS_FAST_CTAS 2
+#define VFGS_FAST_THREADS 1024
+#define VFGS_FAST_CTAS 1
 #endif
 constexpr int kFastThreads = VFGS_FAST_THREADS; // build-time knobs for experiments
 constexpr int kFastWarps = kFastThreads / 32;
@@ -142,7 +143,7 @@ fgs_apply_fast_kernel(const __grid_constant__ FgsParams p)
 
 	// the replicated LUT sits on a 32 KB boundary of the shared window (the launch reserves the slack)
 	uint8_t* lut_ptr = smem + ((0u - smem_u32(smem)) & (uint32_t)(kLutAlign - 1));
-	uint8_t* img_ptr = lut_ptr + kLutBytes;
+	uint8_t* img_ptr = lut_ptr + 3 * kLutBytes;
 
 	if (threadIdx.x == 0) mbar_init(&bar, 1);
 	__syncthreads();
@@ -151,11 +152,7 @@ fgs_apply_fast_kernel(const __grid_constant__ FgsParams p)
 		bulk_copy_g2s(img_ptr, p.fblob, (uint32_t)p.fblob_bytes, &bar);
 	}
 	mbar_wait(&bar, 0);
-	{
-		const uint32_t* compact = (const uint32_t*)img_ptr;
-		uint32_t* lut = (uint32_t*)lut_ptr;
-		for (int i = threadIdx.x; i < 256 * 32; i += kFastThreads) lut[i] = compact[i >> 5];
-	}
+	expand_fast_luts((uint32_t*)lut_ptr, (const uint32_t*)img_ptr, (uint32_t)p.pow16, threadIdx.x, kFastThreads);
 	__syncthreads();
 
 	const int lane = threadIdx.x & 31;

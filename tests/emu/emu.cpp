@@ -14,6 +14,7 @@
 using namespace vfgs;
 
 namespace {
+void f_check(bool ok) { if (!ok) abort(); }
 struct StateDump { // == refh_state / oracle_dump
 	int8_t pattern[2][9][64][64];
 	uint8_t slut[3][256];
@@ -23,10 +24,10 @@ struct StateDump { // == refh_state / oracle_dump
 };
 
 template <bool IN16, bool OUT8>
-void run_fast(const FgsParams& p, const uint8_t* lut, const uint8_t* img)
+void run_fast(const FgsParams& p, const uint8_t* lut)
 {
 	for (long long task = 0; task < p.total_tasks; task++)
-		for (int lane = 0; lane < 32; lane++) process_task_fast<IN16, OUT8>(p, smem_addr(lut), smem_addr(img), (uint32_t)task, lane);
+		for (int lane = 0; lane < 32; lane++) process_task_fast<IN16, OUT8>(p, smem_addr(lut), (uint32_t)task, lane);
 }
 
 template <bool IN16, bool OUT8>
@@ -71,11 +72,11 @@ extern "C" int emu_add_grain_frames(const void* state, const void* in, void* out
 	std::vector<uint32_t> tab_store((blob.size() + 64) / 4);
 	uint8_t* tab = (uint8_t*)tab_store.data();
 	memcpy(tab, blob.data(), blob.size());
-	std::vector<uint8_t> smem_store((size_t)kLutAlign + 3 * kLutBytes + fblob.size() + 64);
-	uint8_t* lut_ptr = (uint8_t*)(((uintptr_t)smem_store.data() + kLutAlign - 1) & ~(uintptr_t)(kLutAlign - 1));
-	uint8_t* img_ptr = lut_ptr + 3 * kLutBytes;
-	memcpy(img_ptr, fblob.data(), fblob.size());
-	expand_fast_luts((uint32_t*)lut_ptr, (const uint32_t*)img_ptr, (uint32_t)(1 << (16 - h.scale_shift)), 0, 1);
+	// the fast kernel's shared window: LUTs on a 32 KB boundary, dynamic shared memory starting kEmuPad bytes
+	// in front of it (1 KB reserved by the driver + 128 B of static variables on the device)
+	constexpr int kEmuPad = kLutAlign - 1152;
+	std::vector<uint8_t> smem_store((size_t)2 * kLutAlign + 3 * kLutBytes + fblob.size() + 64);
+	uint8_t* lut_ptr = (uint8_t*)(((uintptr_t)smem_store.data() + 2 * kLutAlign - 1) & ~(uintptr_t)(kLutAlign - 1));
 
 	// per-block LFSR registers (what lfsr_states_kernel produces)
 	std::vector<uint32_t> states((size_t)nframes * R * spitch, 0);
@@ -109,16 +110,21 @@ extern "C" int emu_add_grain_frames(const void* state, const void* in, void* out
 	finish_tasks(p);
 
 	LaunchPlan lp;
-	plan_launches(p, bi, mode, in == out, 227 * 1024, lp);
+	plan_launches(p, bi, mode, in == out, 227 * 1024, kEmuPad, lp);
 	{ // window offsets of every block (the second table lfsr_states_kernel writes), in the serving kernel's format
 		const WoffParams wp = make_woff_params(p, lp.kind);
 		for (size_t i = 0; i < states.size(); i++)
-			for (int c = 0; c < 3; c++) woffs[i * 4 + c] = (uint16_t)window_offset(c, states[i], wp.off[c], wp.stride[c], wp.subx, wp.suby);
+			for (int c = 0; c < 3; c++) woffs[i * 4 + c] = (uint16_t)window_offset(c, states[i], wp.off[c], wp.stride[c], wp.copy[c], wp.subx, wp.suby);
 	}
-	if (lp.any_fast) {
-		if (isz == 1) run_fast<false, false>(lp.fast, lut_ptr, img_ptr);
-		else if (osz == 1) run_fast<true, true>(lp.fast, lut_ptr, img_ptr);
-		else run_fast<true, false>(lp.fast, lut_ptr, img_ptr);
+	if (lp.any_fast) { // what fgs_apply_fast_kernel builds in shared memory
+		const FgsParams& f = lp.fast;
+		f_check(f.fpad == kEmuPad && f.fsmem <= kEmuPad + 3 * kLutBytes + (int)fblob.size());
+		for (int c = 0; c < 3; c++)
+			if (f.fimg_bytes[c]) memcpy(lut_ptr + f.fimg_off[c], fblob.data() + f.fimg_src[c], (size_t)f.fimg_bytes[c]);
+		expand_fast_luts((uint32_t*)lut_ptr, (const uint32_t*)fblob.data(), (uint32_t)(1 << (16 - h.scale_shift)), 0, 1);
+		if (isz == 1) run_fast<false, false>(f, lut_ptr);
+		else if (osz == 1) run_fast<true, true>(f, lut_ptr);
+		else run_fast<true, false>(f, lut_ptr);
 	}
 	if (lp.any_gather) {
 		// what fgs_apply_gather_kernel builds in shared memory: one private LUT per gather component, then the image

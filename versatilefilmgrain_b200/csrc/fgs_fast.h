@@ -17,6 +17,7 @@
 //     instructions (VIADDMNMX / VIMNMX .S16x2); 10-bit samples stay packed in their load words.
 // Host-compilable like fgs_task.h (tests/emu) -- the helpers below emulate the few PTX instructions.
 #pragma once
+#include <stddef.h>
 #include <type_traits>
 #include "fgs_task.h"
 
@@ -105,8 +106,9 @@ VFGS_HD uint32_t mulhi_u32(uint32_t a, uint32_t b)
 //   lut   uint32 lut[3][256][32]: per component a per-lane replicated LUT of scale << (16 - scale_shift)
 //         (built by the CTA from the compact LUT), each table on a 32 KB boundary of the shared window so
 //         that "lane column | index bits" is a plain OR
-//   img   copy of the global image: uint32 compact_lut[256], then for each component its pattern slot
-//         twice (+ and -), rows packed to fpat_stride bytes; fpat_off is relative to img
+//   img   per component its pattern slot as +pattern and -pattern, each in column-shifted copies
+//         (fast_copies), rows packed to fpat_stride bytes; the image of component c starts fimg_off[c] bytes
+//         from the first LUT (in front of it or behind the third one), fpat_off is relative to that
 // Addresses are absolute: 32-bit shared-window addresses on the device, pointers in the host build.
 constexpr int kLutBytes = 256 * 32 * 4;
 constexpr int kLutAlign = 32768;
@@ -125,12 +127,14 @@ VFGS_HD void expand_fast_luts(uint32_t* lut, const uint32_t* compact, uint32_t p
 typedef uint32_t smem_addr_t;
 __device__ __forceinline__ smem_addr_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t lds32(smem_addr_t a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void lds64(smem_addr_t a, uint32_t& lo, uint32_t& hi) { asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(a)); }
 __device__ __forceinline__ int lds_s8(smem_addr_t a) { int v; asm("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ int lds_u8(smem_addr_t a) { int v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 #else
 typedef uintptr_t smem_addr_t;
 inline smem_addr_t smem_addr(const void* p) { return (uintptr_t)p; }
 inline uint32_t lds32(smem_addr_t a) { return *(const uint32_t*)a; }
+inline void lds64(smem_addr_t a, uint32_t& lo, uint32_t& hi) { lo = ((const uint32_t*)a)[0]; hi = ((const uint32_t*)a)[1]; }
 inline int lds_s8(smem_addr_t a) { return (int)*(const int8_t*)a; }
 inline int lds_u8(smem_addr_t a) { return (int)*(const uint8_t*)a; }
 #endif
@@ -138,6 +142,9 @@ inline int lds_u8(smem_addr_t a) { return (int)*(const uint8_t*)a; }
 // Measured on B200 (scripts/variant_sweep.sh): with 16-bit output the fast kernel is HBM-bound and runs
 // ~2 % faster when the sample loads allocate in L1 (whole 128-byte lines are brought in ahead of the
 // neighbouring lanes' requests); with 8-bit output it is issue-bound and the streaming operator is ahead.
+#ifndef VFGS_FAST_L1_MODE
+#define VFGS_FAST_L1_MODE 1 // 0: never, 1: with 16-bit output, 2: always (build-time knob for experiments)
+#endif
 template <bool L1_ALLOCATE>
 VFGS_HD void ld_samples_16(const uint8_t* p, uint32_t r[4])
 {
@@ -183,27 +190,28 @@ VFGS_HD void ld_global_8_if(const uint8_t* p, uint32_t r[2], bool pred)
 #endif
 }
 
-// 8 consecutive pattern bytes at address a; ALIGNED: a % 4 == 0 (luma-type components), else
-// a % 4 in {0, 2} (horizontally subsampled chroma: ox is a multiple of 2).
-template <bool ALIGNED>
+// 8 consecutive pattern bytes at address a, a % 8 == 0: the image holds every pattern in as many
+// column-shifted copies as the window column has residues modulo 8 (fast_copies), and the block's window
+// offset (window_offset) selects the copy in which the window starts on an 8-byte boundary.
+#ifndef VFGS_FAST_LDS64
+#define VFGS_FAST_LDS64 1 // build-time knob for experiments
+#endif
 VFGS_HD void octet(smem_addr_t a, uint32_t& w0, uint32_t& w1)
 {
-	if (ALIGNED) {
-		w0 = lds32(a); w1 = lds32(a + 4);
-	} else {
-		const smem_addr_t al = a & ~(smem_addr_t)3;
-		const int sh = (int)(a & 3) * 8;
-		const uint32_t x0 = lds32(al), x1 = lds32(al + 4), x2 = lds32(al + 8);
-#if defined(__CUDA_ARCH__)
-		w0 = __funnelshift_r(x0, x1, sh); w1 = __funnelshift_r(x1, x2, sh);
-#else
-		w0 = sh ? (x0 >> sh) | (x1 << (32 - sh)) : x0;
-		w1 = sh ? (x1 >> sh) | (x2 << (32 - sh)) : x1;
-#endif
-	}
+	if (VFGS_FAST_LDS64) lds64(a, w0, w1);
+	else { w0 = lds32(a); w1 = lds32(a + 4); }
 }
 
 // Per-lane constants of a warp-task (pattern addresses have the block's sign folded in).
+// Halo bytes feed the block-edge filter. With 16-sample blocks a lane holds one half of a block and has
+// exactly one block edge (its left end if it is the first half, else its right end), so one halo address
+// and one filter can serve (MergeHalo): lh. With 8-sample blocks the lane is a whole block and has both.
+// Measured on B200 (scripts/ab_sweep.sh, same box): the merged form is +3 points of HBM roofline for the
+// issue-bound 8-bit-output kernel and -4 points for the HBM-bound 16-bit-output kernel, hence mode 2.
+#ifndef VFGS_FAST_MERGE_HALO
+#define VFGS_FAST_MERGE_HALO 2 // 0 never, 1 always, 2 only with 8-bit output
+#endif
+template <bool OUT8> struct MergeHalo { static constexpr bool value = VFGS_FAST_MERGE_HALO == 1 || (VFGS_FAST_MERGE_HALO == 2 && OUT8); };
 struct FastLane {
 	smem_addr_t own;         // the lane's octet, pattern row of line j = 0 of the current block
 	smem_addr_t lh, rh;      // halo bytes: last column of block b-1 / first column of block b+1
@@ -231,32 +239,47 @@ template <bool IN16, bool OUT8, int NSH>
 VFGS_HD void fast_line(const FastLane& L, int rc, int w_cur, int w_up, const FastUp& U, int ru,
                        const uint32_t raw[4], uint32_t outw[4])
 {
-	constexpr bool ALIGNED = NSH == 4;
 	uint32_t c0, c1;
-	octet<ALIGNED>(L.own + rc, c0, c1);
+	octet(L.own + rc, c0, c1);
 	int g[8];
 	g[0] = octet_byte<0>(c0, c1); g[1] = octet_byte<1>(c0, c1); g[2] = octet_byte<2>(c0, c1); g[3] = octet_byte<3>(c0, c1);
 	g[4] = octet_byte<4>(c0, c1); g[5] = octet_byte<5>(c0, c1); g[6] = octet_byte<6>(c0, c1); g[7] = octet_byte<7>(c0, c1);
-	int hl = L.has_left ? lds_s8(L.lh + rc) : 0;
-	int hr = L.has_right ? lds_s8(L.rh + rc) : 0;
-
-	// vertical overlap with the block-row above (vfgs_hw.c:173-188, 223-229)
-	if (w_cur) {
-		uint32_t u0, u1;
-		octet<ALIGNED>(U.own + ru, u0, u1);
-		g[0] = blend<0>(g[0], u0, u1, w_cur, w_up); g[1] = blend<1>(g[1], u0, u1, w_cur, w_up);
-		g[2] = blend<2>(g[2], u0, u1, w_cur, w_up); g[3] = blend<3>(g[3], u0, u1, w_cur, w_up);
-		g[4] = blend<4>(g[4], u0, u1, w_cur, w_up); g[5] = blend<5>(g[5], u0, u1, w_cur, w_up);
-		g[6] = blend<6>(g[6], u0, u1, w_cur, w_up); g[7] = blend<7>(g[7], u0, u1, w_cur, w_up);
-		if (L.has_left) hl = (hl * w_cur + lds_s8(U.lh + ru) * w_up + 16) >> 5;
-		if (L.has_right) hr = (hr * w_cur + lds_s8(U.rh + ru) * w_up + 16) >> 5;
+	if (MergeHalo<OUT8>::value && NSH == 4) {
+		// one edge per lane: halo h next to a, then b (left edge: h | g0 g1, right edge: g6 g7 | h mirrored)
+		const bool edge = L.has_left || L.has_right;
+		int h = edge ? lds_s8(L.lh + rc) : 0;
+		if (w_cur) { // vertical overlap with the block-row above (vfgs_hw.c:173-188, 223-229)
+			uint32_t u0, u1;
+			octet(U.own + ru, u0, u1);
+			g[0] = blend<0>(g[0], u0, u1, w_cur, w_up); g[1] = blend<1>(g[1], u0, u1, w_cur, w_up);
+			g[2] = blend<2>(g[2], u0, u1, w_cur, w_up); g[3] = blend<3>(g[3], u0, u1, w_cur, w_up);
+			g[4] = blend<4>(g[4], u0, u1, w_cur, w_up); g[5] = blend<5>(g[5], u0, u1, w_cur, w_up);
+			g[6] = blend<6>(g[6], u0, u1, w_cur, w_up); g[7] = blend<7>(g[7], u0, u1, w_cur, w_up);
+			if (edge) h = (h * w_cur + lds_s8(U.lh + ru) * w_up + 16) >> 5;
+		}
+		// block-edge filter (vfgs_hw.c:250-259), taps read unfiltered grain
+		const int a = L.has_right ? g[7] : g[0], b = L.has_right ? g[6] : g[1];
+		const int f = (h + 3 * a + b + 2) >> 2;
+		g[0] = L.has_left ? f : g[0];
+		g[7] = L.has_right ? f : g[7];
+	} else {
+		int hl = L.has_left ? lds_s8(L.lh + rc) : 0;
+		int hr = L.has_right ? lds_s8(L.rh + rc) : 0;
+		if (w_cur) {
+			uint32_t u0, u1;
+			octet(U.own + ru, u0, u1);
+			g[0] = blend<0>(g[0], u0, u1, w_cur, w_up); g[1] = blend<1>(g[1], u0, u1, w_cur, w_up);
+			g[2] = blend<2>(g[2], u0, u1, w_cur, w_up); g[3] = blend<3>(g[3], u0, u1, w_cur, w_up);
+			g[4] = blend<4>(g[4], u0, u1, w_cur, w_up); g[5] = blend<5>(g[5], u0, u1, w_cur, w_up);
+			g[6] = blend<6>(g[6], u0, u1, w_cur, w_up); g[7] = blend<7>(g[7], u0, u1, w_cur, w_up);
+			if (L.has_left) hl = (hl * w_cur + lds_s8(U.lh + ru) * w_up + 16) >> 5;
+			if (L.has_right) hr = (hr * w_cur + lds_s8(U.rh + ru) * w_up + 16) >> 5;
+		}
+		const int f0 = (hl + 3 * g[0] + g[1] + 2) >> 2;
+		const int f7 = (g[6] + 3 * g[7] + hr + 2) >> 2;
+		g[0] = L.has_left ? f0 : g[0];
+		g[7] = L.has_right ? f7 : g[7];
 	}
-
-	// block-edge filter (vfgs_hw.c:250-259), taps read unfiltered grain
-	const int f0 = (hl + 3 * g[0] + g[1] + 2) >> 2;
-	const int f7 = (g[6] + 3 * g[7] + hr + 2) >> 2;
-	g[0] = L.has_left ? f0 : g[0];
-	g[7] = L.has_right ? f7 : g[7];
 
 	// scale * grain, rounded shift (vfgs_hw.c:263): the LUT holds scale * 2^(16 - shift), so the rounded
 	// quotient is exactly the upper half-word of lut * grain + 0x8000
@@ -304,27 +327,44 @@ VFGS_HD void fast_line(const FastLane& L, int rc, int w_cur, int w_up, const Fas
 	}
 }
 
+// Column-shifted copies of a pattern in the fast image: the window column ox is a multiple of 4 for
+// 16-sample blocks (copies shifted by 0 and 4 bytes) and of 2 for 8-sample blocks (0, 2, 4, 6).
+VFGS_HD int fast_copies(int block_samples) { return block_samples == 16 ? 2 : 4; }
+
 // Byte offset, inside the fast image, of a block's pattern window for component c: the +pattern or
-// -pattern copy according to the block's sign, row oy, column ox. Precomputed per block by
-// lfsr_states_kernel (FgsParams::woffs), so a lane only adds its column and the line's row pitch.
-VFGS_HD uint32_t window_offset(int c, uint32_t state, const int off[2], int stride, int subx, int suby)
+// -pattern copies according to the block's sign, among them the copy shifted by ox % 8 bytes (copy_bytes
+// apart), row oy, column ox rounded down to 8. copy_bytes == 0: plain oy * stride + ox (the gather kernel's
+// format). Precomputed per block by lfsr_states_kernel (FgsParams::woffs), so a lane only adds its column
+// and the line's row pitch.
+VFGS_HD uint32_t window_offset(int c, uint32_t state, const int off[2], int stride, int copy_bytes, int subx, int suby)
 {
 	const BlockOfs o = decode_offsets(c, state, subx, suby);
-	return (uint32_t)(off[o.sign < 0 ? 1 : 0] + o.oy * stride + o.ox);
+	const int base = off[o.sign < 0 ? 1 : 0] + o.oy * stride;
+	if (!copy_bytes) return (uint32_t)(base + o.ox);
+	const int k = (c && subx > 1) ? (o.ox >> 1) & 3 : (o.ox >> 2) & 1;
+	return (uint32_t)(base + k * copy_bytes + (o.ox & ~7));
 }
 
 #ifndef VFGS_FAST_LB
 #define VFGS_FAST_LB 4
 #endif
 constexpr int kFastLB = VFGS_FAST_LB; // lines in flight per lane (build-time knob for experiments)
+#ifndef VFGS_FAST_LB16
+#define VFGS_FAST_LB16 VFGS_FAST_LB // fast kernel, 16-bit (or 8-bit in, 8-bit out) stores
+#endif
+#ifndef VFGS_FAST_LB8
+#define VFGS_FAST_LB8 VFGS_FAST_LB  // fast kernel, 16-bit in, 8-bit out
+#endif
 
 template <bool IN16, bool OUT8, int NSH>
-VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, smem_addr_t img, const TaskGeom& t, int k0, int lane)
+VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, const TaskGeom& t, int k0, int lane)
 {
 	const int c = t.c;
+	const smem_addr_t img = lut + (smem_addr_t)(ptrdiff_t)p.fimg_off[c]; // the component's pattern image
 	const Plane& pl = p.comp[c];
 	const int ysh = (c && p.suby > 1) ? 1 : 0;
 	constexpr int n = 1 << NSH;
+	constexpr int LB = OUT8 ? VFGS_FAST_LB8 : VFGS_FAST_LB16; // lines in flight per lane
 
 	// component lines of this stripe (whole stripes only: the host sends partial line ranges to
 	// the general kernel)
@@ -335,17 +375,18 @@ VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, smem_addr_t img
 	if (nl <= 0) return;
 
 	constexpr int IB = IN16 ? 2 : 1, OB = (IN16 && !OUT8) ? 2 : 1;
+	constexpr bool kL1 = VFGS_FAST_L1_MODE == 2 || (VFGS_FAST_L1_MODE == 1 && !OUT8); // sample loads allocate in L1
 	const long long in_pitch = pl.in_row_bytes, out_pitch = pl.out_row_bytes;
 	const uint8_t* src = pl.in + (long long)t.f * p.in_frame_bytes + (long long)cl0 * in_pitch + (long long)k0 * IB;
 	uint8_t* dst = pl.out + (long long)t.f * p.out_frame_bytes + (long long)cl0 * out_pitch + (long long)k0 * OB;
 
-	// The first kFastLB lines are requested before anything else: the block decode below runs
-	// while they are in flight. A stripe shorter than kFastLB lines re-reads its last line.
-	uint32_t raw[kFastLB][4];
+	// The first LB lines are requested before anything else: the block decode below runs
+	// while they are in flight. A stripe shorter than LB lines re-reads its last line.
+	uint32_t raw[LB][4];
 #pragma unroll
-	for (int q = 0; q < kFastLB; q++) {
+	for (int q = 0; q < LB; q++) {
 		const int qq = q < nl ? q : nl - 1;
-		if (IN16) ld_samples_16<!OUT8>(src + qq * in_pitch, raw[q]);
+		if (IN16) ld_samples_16<kL1>(src + qq * in_pitch, raw[q]);
 		else ld_global_8(src + qq * in_pitch, raw[q]);
 	}
 
@@ -364,7 +405,7 @@ VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, smem_addr_t img
 	L.own = img + (smem_addr_t)(w_cur[0] + i0);
 	L.lh = L.rh = L.own;
 	if (L.has_left) L.lh = img + (smem_addr_t)(w_cur[-4] + n - 1);
-	if (L.has_right) L.rh = img + (smem_addr_t)w_cur[4];
+	if (L.has_right) (MergeHalo<OUT8>::value && NSH == 4 ? L.lh : L.rh) = img + (smem_addr_t)w_cur[4];
 
 	// the first lines of a stripe overlap the block-row above (never in the first stripe, y <= 15)
 	FastUp U;
@@ -374,29 +415,29 @@ VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, smem_addr_t img
 		const uint16_t* w_up = w_cur - p.spitch * 4;
 		U.own = img + (smem_addr_t)(w_up[0] + i0);
 		if (L.has_left) U.lh = img + (smem_addr_t)(w_up[-4] + n - 1);
-		if (L.has_right) U.rh = img + (smem_addr_t)w_up[4];
+		if (L.has_right) (MergeHalo<OUT8>::value && NSH == 4 ? U.lh : U.rh) = img + (smem_addr_t)w_up[4];
 	}
 
 	int rc = 0;
-	const uint8_t* nxt = src + kFastLB * in_pitch; // line whose load refills the slot just consumed
-	// WHOLE: the stripe is a whole number of kFastLB-line groups (every stripe of a picture whose height is a
-	// multiple of kFastLB component lines): no per-line store predicate, one refill predicate per group.
+	const uint8_t* nxt = src + LB * in_pitch; // line whose load refills the slot just consumed
+	// WHOLE: the stripe is a whole number of LB-line groups (every stripe of a picture whose height is a
+	// multiple of LB component lines): no per-line store predicate, one refill predicate per group.
 	auto lines = [&](auto whole_tag) {
 		constexpr bool WHOLE = decltype(whole_tag)::value;
 #pragma unroll 1
-		for (int base = 0; base < nl; base += kFastLB) {
-			const bool more = base + kFastLB < nl;
+		for (int base = 0; base < nl; base += LB) {
+			const bool more = base + LB < nl;
 #pragma unroll
-			for (int q = 0; q < kFastLB; q++) {
+			for (int q = 0; q < LB; q++) {
 				const int line = base + q;
 				uint32_t w[4];
 				int w_cur = 0, w_up = 0, ru = 0;
 				if (q == 0 && ovl) { w_cur = ysh ? 20 : 12; w_up = ysh ? 20 : 24; ru = (16 >> ysh) * L.stride; }
 				if (q == 1 && ovl && !ysh) { w_cur = 24; w_up = 12; ru = 17 * L.stride; }
 				fast_line<IN16, OUT8, NSH>(L, rc, w_cur, w_up, U, ru, raw[q], w);
-				// this slot's registers are free again: request the line kFastLB further down
-				const bool refill = WHOLE ? more : line + kFastLB < nl;
-				if (IN16) ld_samples_16_if<!OUT8>(nxt, raw[q], refill);
+				// this slot's registers are free again: request the line LB further down
+				const bool refill = WHOLE ? more : line + LB < nl;
+				if (IN16) ld_samples_16_if<kL1>(nxt, raw[q], refill);
 				else ld_global_8_if(nxt, raw[q], refill);
 				if (WHOLE || line < nl) {
 					if (OB == 2) st_global_16(dst, w);
@@ -407,7 +448,7 @@ VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, smem_addr_t img
 			ovl = false;
 		}
 	};
-	if (nl % kFastLB == 0) lines(std::true_type());
+	if (nl % LB == 0) lines(std::true_type());
 	else lines(std::false_type());
 }
 
@@ -417,7 +458,7 @@ VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, smem_addr_t img
 // stripes' rows are one flat run of lane units (8 samples), 32 consecutive units per warp-task, so only
 // the very last task of a component can have idle lanes (a row need not be a multiple of 256 samples).
 template <bool IN16, bool OUT8>
-VFGS_HD void process_task_fast(const FgsParams& p, smem_addr_t lut, smem_addr_t img, uint32_t task, int lane)
+VFGS_HD void process_task_fast(const FgsParams& p, smem_addr_t lut, uint32_t task, int lane)
 {
 	TaskGeom t;
 	t.f = (int)fastdiv(task, p.div_ftasks);
@@ -432,8 +473,8 @@ VFGS_HD void process_task_fast(const FgsParams& p, smem_addr_t lut, smem_addr_t 
 	t.r = p.row_begin + (int)row;
 	t.seg = 0;
 	const int k0 = (int)(unit - row * upr) * kSamplesPerLane;
-	if (t.c && p.subx > 1) fast_task_body<IN16, OUT8, 3>(p, lut, img, t, k0, lane);
-	else fast_task_body<IN16, OUT8, 4>(p, lut, img, t, k0, lane);
+	if (t.c && p.subx > 1) fast_task_body<IN16, OUT8, 3>(p, lut, t, k0, lane);
+	else fast_task_body<IN16, OUT8, 4>(p, lut, t, k0, lane);
 }
 
 } // namespace vfgs

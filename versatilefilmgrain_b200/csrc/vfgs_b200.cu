@@ -35,6 +35,7 @@ struct Context {
 	int device = -1;
 	int sm_count = 0;
 	int max_smem_optin = 0;
+	int fast_pad = 0;           // gap between the fast kernel's dynamic shared memory and the next 32 KB boundary
 	uint32_t* d_pow2 = nullptr;
 	uint8_t* d_blob = nullptr;
 	size_t blob_cap = 0;
@@ -124,6 +125,15 @@ int ensure_ctx(int device)
 	c.device = device;
 	c.sm_count = prop.multiProcessorCount;
 	c.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+	{ // where the fast kernel's dynamic shared memory starts inside the shared window: behind the driver's
+	  // reserved bytes and the kernel's static variables (the kernel traps if this guess is off)
+		int reserved = 0;
+		CUDA_TRY(cudaDeviceGetAttribute(&reserved, cudaDevAttrReservedSharedMemoryPerBlock, device));
+		cudaFuncAttributes fa;
+		CUDA_TRY(cudaFuncGetAttributes(&fa, fgs_apply_fast_kernel<true, false>));
+		const int base = reserved + ((int)fa.sharedSizeBytes + 127) / 128 * 128;
+		c.fast_pad = (kLutAlign - base % kLutAlign) % kLutAlign;
+	}
 	CUDA_TRY(cudaMalloc(&c.d_pow2, sizeof(uint32_t) * kJumpBits * 32));
 	CUDA_TRY(cudaMemcpy(c.d_pow2, jump_table().pow2, sizeof(uint32_t) * kJumpBits * 32, cudaMemcpyHostToDevice));
 	CUDA_TRY(cudaStreamCreateWithFlags(&c.s_h2d, cudaStreamNonBlocking));
@@ -171,13 +181,6 @@ int upload_blob()
 	}
 	if (int rc = grow(c.d_fblob, c.fblob_cap, (size_t)g_bi.fbytes)) return rc;
 	CUDA_TRY(cudaMemcpy(c.d_fblob, g_fblob.data(), (size_t)g_bi.fbytes, cudaMemcpyHostToDevice));
-	if (kLutAlign + 3 * kLutBytes + g_bi.fbytes > c.fast_smem_attr) {
-		const int need = kLutAlign + 3 * kLutBytes + g_bi.fbytes;
-		CUDA_TRY(cudaFuncSetAttribute(fgs_apply_fast_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
-		CUDA_TRY(cudaFuncSetAttribute(fgs_apply_fast_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
-		CUDA_TRY(cudaFuncSetAttribute(fgs_apply_fast_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
-		c.fast_smem_attr = need;
-	}
 	g_dirty = false;
 	return VFGS_B200_OK;
 }
@@ -237,7 +240,13 @@ int launch_apply(const FgsParams& p, cudaStream_t stream, KernelKind kind = kGen
 	if (kind == kFast) {
 		kern = p.in_bytes == 1 ? fgs_apply_fast_kernel<false, false>
 		     : p.out_bytes == 1 ? fgs_apply_fast_kernel<true, true> : fgs_apply_fast_kernel<true, false>;
-		threads = kFastThreads; smem = kLutAlign + 3 * kLutBytes + p.fblob_bytes; // slack to place the LUTs on a 32 KB boundary
+		threads = kFastThreads; smem = p.fsmem;
+		if (smem > c.fast_smem_attr) {
+			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_fast_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_fast_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_fast_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+			c.fast_smem_attr = smem;
+		}
 	} else if (kind == kGather) {
 		kern = p.in_bytes == 1 ? fgs_apply_gather_kernel<false, false>
 		     : p.out_bytes == 1 ? fgs_apply_gather_kernel<true, true> : fgs_apply_gather_kernel<true, false>;
@@ -328,7 +337,7 @@ int run_frames_device(const vfgs_b200_planes& in, const vfgs_b200_planes& out, i
 	// every component goes to the cheapest kernel that can serve it (plan_launches)
 	g_ctx.last_launch[4] = 0;
 	LaunchPlan lp;
-	plan_launches(p, g_bi, g_kernel_mode, in.y == out.y, g_ctx.max_smem_optin - 1024, lp);
+	plan_launches(p, g_bi, g_kernel_mode, in.y == out.y, g_ctx.max_smem_optin - 1024, g_ctx.fast_pad, lp);
 	if (int rc = launch_streams(epoch, d_streams, d_woffs, make_woff_params(p, lp.kind), n, g, frame0, stream)) return rc;
 	if (lp.any_fast)
 		if (int rc = launch_apply(lp.fast, stream, kFast)) return rc;

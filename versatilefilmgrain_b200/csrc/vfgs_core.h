@@ -178,12 +178,19 @@ struct FgsParams {
 	int pat_off[2];         // luma / chroma pattern slots
 	int pat_size[2];        // bytes per slot
 	int pat_stride[2];      // bytes per pattern row
-	// table image of the fast path (fgs_fast.h): uint32 lut[256] = sLUT[Y] | sLUT[U]<<8 | sLUT[V]<<16, then
-	// per component its single pattern slot twice (+pattern, -pattern)
+	// table image of the fast path (fgs_fast.h), in global memory: uint32 lut[256] = sLUT[Y] | sLUT[U]<<8 | sLUT[V]<<16,
+	// then per component its single pattern slot as +pattern and -pattern, each in column-shifted copies.
+	// In shared memory the three expanded LUTs sit on 32 KB boundaries of the shared window; the component
+	// images go into the gap in front of the first LUT as far as they fit, the rest behind the last LUT.
 	const uint8_t* fblob;
-	int fblob_bytes;
-	int fpat_off[3][2];     // byte offsets inside the kernel's shared memory (after the expanded LUT)
+	int fimg_src[3];        // byte offset of the component's image inside fblob
+	int fimg_bytes[3];      // its size (0: the component is not served by the fast kernel)
+	int fimg_off[3];        // where it goes in shared memory, relative to the first LUT (negative: in front of it)
+	int fpad;               // bytes between the start of dynamic shared memory and the first LUT (checked by the kernel)
+	int fsmem;              // dynamic shared memory of the launch
+	int fpat_off[3][2];     // +pattern / -pattern copies, relative to the component's image
 	int fpat_stride[3];
+	int fpat_copy[3];       // bytes between the column-shifted copies of a pattern
 	// gather path (fgs_gather.h): private LUT slot of each component (-1: none) and the pattern banks'
 	// offsets inside the general image
 	int glut_index[3], ngather;

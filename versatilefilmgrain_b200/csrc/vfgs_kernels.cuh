@@ -92,7 +92,7 @@ lfsr_states_kernel(uint32_t epoch_state, const uint32_t* __restrict__ pow2, uint
 			dst[1 + b0 + lane] = st;
 			if (woffs) { // pattern-window offsets of the block for the fast path, one 8-byte store
 				uint32_t o[3];
-				for (int c = 0; c < 3; c++) o[c] = window_offset(c, st, wp.off[c], wp.stride[c], wp.subx, wp.suby); // fast or gather format
+				for (int c = 0; c < 3; c++) o[c] = window_offset(c, st, wp.off[c], wp.stride[c], wp.copy[c], wp.subx, wp.suby); // fast or gather format
 				uint2 v;
 				v.x = o[0] | (o[1] << 16); v.y = o[2];
 				*(uint2*)(woffs + ((size_t)warp * spitch + 1 + b0 + lane) * 4) = v;
@@ -124,9 +124,12 @@ fgs_apply_kernel(const __grid_constant__ FgsParams p)
 }
 
 // Fast path: single-pattern components, aligned rows (fgs_fast.h). One 1024-thread persistent CTA per
-// SM (measured faster than 2 x 512: one table image per SM, more of the unified array left to L1);
-// shared memory = three per-lane replicated LUTs of scale << (16 - shift) (3 x 32 KB, expanded here from
-// the 1 KB compact LUT) + the +/- pattern copies, brought in by one bulk async copy.
+// SM (measured faster than 2 x 512: one table image per SM, more of the unified array left to L1, which
+// the 16-bit-output variant uses as its landing buffer for the lines in flight).
+// Shared memory: three per-lane replicated LUTs of scale << (16 - shift) (3 x 32 KB, each on a 32 KB
+// boundary of the shared window, expanded here from the 1 KB compact LUT in global memory) and the
+// components' +/- pattern copies, brought in by bulk async copies: in the gap between the start of dynamic
+// shared memory and the first LUT as far as they fit (FgsParams::fimg_off < 0), else behind the third LUT.
 #ifndef VFGS_FAST_THREADS
 #define VFGS_FAST_THREADS 1024
 #define VFGS_FAST_CTAS 1
@@ -141,25 +144,27 @@ fgs_apply_fast_kernel(const __grid_constant__ FgsParams p)
 	extern __shared__ __align__(128) uint8_t smem[];
 	__shared__ __align__(8) uint64_t bar;
 
-	// the replicated LUT sits on a 32 KB boundary of the shared window (the launch reserves the slack)
-	uint8_t* lut_ptr = smem + ((0u - smem_u32(smem)) & (uint32_t)(kLutAlign - 1));
-	uint8_t* img_ptr = lut_ptr + 3 * kLutBytes;
+	// the host laid the images out for the gap it expects in front of the first LUT
+	const uint32_t pad = (0u - smem_u32(smem)) & (uint32_t)(kLutAlign - 1);
+	if (pad != (uint32_t)p.fpad) __trap();
+	uint8_t* lut_ptr = smem + pad;
 
 	if (threadIdx.x == 0) mbar_init(&bar, 1);
 	__syncthreads();
 	if (threadIdx.x == 0) {
-		mbar_arrive_expect_tx(&bar, (uint32_t)p.fblob_bytes);
-		bulk_copy_g2s(img_ptr, p.fblob, (uint32_t)p.fblob_bytes, &bar);
+		mbar_arrive_expect_tx(&bar, (uint32_t)(p.fimg_bytes[0] + p.fimg_bytes[1] + p.fimg_bytes[2]));
+		for (int c = 0; c < 3; c++)
+			if (p.fimg_bytes[c]) bulk_copy_g2s(lut_ptr + p.fimg_off[c], p.fblob + p.fimg_src[c], (uint32_t)p.fimg_bytes[c], &bar);
 	}
+	expand_fast_luts((uint32_t*)lut_ptr, (const uint32_t*)p.fblob, (uint32_t)p.pow16, threadIdx.x, kFastThreads);
 	mbar_wait(&bar, 0);
-	expand_fast_luts((uint32_t*)lut_ptr, (const uint32_t*)img_ptr, (uint32_t)p.pow16, threadIdx.x, kFastThreads);
 	__syncthreads();
 
 	const int lane = threadIdx.x & 31;
-	const smem_addr_t lut = smem_addr(lut_ptr), img = smem_addr(img_ptr);
+	const smem_addr_t lut = smem_addr(lut_ptr);
 	const long long stride = (long long)gridDim.x * kFastWarps;
 	for (long long task = (long long)blockIdx.x * kFastWarps + (threadIdx.x >> 5); task < p.total_tasks; task += stride)
-		process_task_fast<IN16, OUT8>(p, lut, img, (uint32_t)task, lane);
+		process_task_fast<IN16, OUT8>(p, lut, (uint32_t)task, lane);
 }
 
 // Gather path: components with sample-adaptive pattern selection (fgs_gather.h). Shared memory: one

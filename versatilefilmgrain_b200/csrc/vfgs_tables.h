@@ -39,7 +39,8 @@ struct TableInfo {
 	// fast image (fgs_fast.h): usable for a component when its pattern LUT selects one slot and that
 	// slot has no -128 byte (so that -pattern fits int8)
 	bool fast_ok[3];
-	int fpat_off[3][2], fpat_stride[3], fbytes;
+	int fimg_src[3], fimg_bytes[3]; // component images inside the fast image (bytes 0 when !fast_ok)
+	int fpat_off[3][2], fpat_stride[3], fpat_copy[3], fbytes; // fpat_off: relative to the component image; fpat_copy: bytes from one column-shifted copy to the next
 };
 
 // General image layout (all offsets multiples of 16): LUT uint16[3][256] = scale | slot << 8, then the
@@ -72,10 +73,13 @@ inline void build_tables(const HwState& h, TableInfo& g_bi, std::vector<uint8_t>
 		for (int r = 0; r < crows; r++)
 			memcpy(&g_blob[g_bi.pat_off[1] + s * g_bi.pat_size[1] + r * ccols], h.pattern[1][s][r], (size_t)ccols);
 
-	// fast-path image: compact scale LUT, then +pattern / -pattern of each component's single slot
+	// fast-path image: compact scale LUT, then per component the single slot as +pattern and -pattern, each in
+	// fast_copies() column-shifted copies (copy k holds the pattern moved left by k * 8 / copies bytes), so that
+	// every window column has a copy in which it sits on an 8-byte boundary (fgs_fast.h, window_offset)
 	int off = 256 * 4;
 	for (int c = 0; c < 3; c++) {
 		const int rows = c ? crows : 64, cols = c ? ccols : 64;
+		const int ncopy = fast_copies((c && h.csubx > 1) ? 8 : 16);
 		const int slot = g_bi.uniform_pi[c];
 		bool ok = slot >= 0;
 		for (int r = 0; ok && r < rows; r++)
@@ -83,24 +87,31 @@ inline void build_tables(const HwState& h, TableInfo& g_bi, std::vector<uint8_t>
 				if (h.pattern[c ? 1 : 0][slot][r][x] == -128) { ok = false; break; }
 		g_bi.fast_ok[c] = ok;
 		g_bi.fpat_stride[c] = cols;
-		g_bi.fpat_off[c][0] = off;
-		g_bi.fpat_off[c][1] = off + rows * cols;
-		off += 2 * rows * cols;
+		g_bi.fpat_copy[c] = rows * cols;
+		g_bi.fpat_off[c][0] = 0;
+		g_bi.fpat_off[c][1] = ncopy * rows * cols;
+		g_bi.fimg_src[c] = off;
+		g_bi.fimg_bytes[c] = ok ? 2 * ncopy * rows * cols : 0;
+		if (c == 2 && ok && g_bi.fast_ok[1] && g_bi.uniform_pi[1] == slot) g_bi.fimg_src[2] = g_bi.fimg_src[1]; // Cb and Cr read the same slot: one image
+		else off += g_bi.fimg_bytes[c];
 	}
-	g_bi.fbytes = (off + 16 + 15) & ~15; // +16: the unaligned octet fetch may touch one word past a row
+	g_bi.fbytes = (off + 15) & ~15;
 	g_fblob.assign((size_t)g_bi.fbytes, 0);
 	uint32_t* clut = (uint32_t*)g_fblob.data();
 	for (int i = 0; i < 256; i++) clut[i] = (uint32_t)h.slut[0][i] | ((uint32_t)h.slut[1][i] << 8) | ((uint32_t)h.slut[2][i] << 16);
 	for (int c = 0; c < 3; c++) {
-		if (!g_bi.fast_ok[c]) continue;
+		if (!g_bi.fast_ok[c] || (c == 2 && g_bi.fimg_src[2] == g_bi.fimg_src[1])) continue;
 		const int rows = c ? crows : 64, cols = c ? ccols : 64;
-		int8_t* plus = (int8_t*)&g_fblob[g_bi.fpat_off[c][0]];
-		int8_t* minus = (int8_t*)&g_fblob[g_bi.fpat_off[c][1]];
-		for (int r = 0; r < rows; r++)
-			for (int x = 0; x < cols; x++) {
-				const int8_t v = h.pattern[c ? 1 : 0][g_bi.uniform_pi[c]][r][x];
-				plus[r * cols + x] = v; minus[r * cols + x] = (int8_t)-v;
-			}
+		const int ncopy = fast_copies((c && h.csubx > 1) ? 8 : 16), shift = 8 / ncopy;
+		for (int k = 0; k < ncopy; k++) {
+			int8_t* plus = (int8_t*)&g_fblob[g_bi.fimg_src[c] + g_bi.fpat_off[c][0] + k * rows * cols];
+			int8_t* minus = (int8_t*)&g_fblob[g_bi.fimg_src[c] + g_bi.fpat_off[c][1] + k * rows * cols];
+			for (int r = 0; r < rows; r++)
+				for (int x = 0; x + k * shift < cols; x++) {
+					const int8_t v = h.pattern[c ? 1 : 0][g_bi.uniform_pi[c]][r][x + k * shift];
+					plus[r * cols + x] = v; minus[r * cols + x] = (int8_t)-v;
+				}
+		}
 	}
 }
 
@@ -118,8 +129,10 @@ inline void fill_state_params(FgsParams& p, const HwState& h, const TableInfo& b
 		p.uniform_pi[c] = bi.uniform_pi[c];
 		p.fpat_off[c][0] = bi.fpat_off[c][0]; p.fpat_off[c][1] = bi.fpat_off[c][1];
 		p.fpat_stride[c] = bi.fpat_stride[c];
+		p.fpat_copy[c] = bi.fpat_copy[c];
+		p.fimg_src[c] = bi.fimg_src[c]; p.fimg_bytes[c] = bi.fimg_bytes[c];
 	}
-	p.blob_bytes = bi.bytes; p.fblob_bytes = bi.fbytes;
+	p.blob_bytes = bi.bytes;
 	p.lut_off = bi.lut_off;
 	for (int b = 0; b < 2; b++) { p.pat_off[b] = bi.pat_off[b]; p.pat_size[b] = bi.pat_size[b]; p.pat_stride[b] = bi.pat_stride[b]; }
 }
@@ -143,6 +156,33 @@ inline void finish_tasks(FgsParams& p)
 	p.div_rows = make_fastdiv((uint32_t)(p.rows > 0 ? p.rows : 1));
 }
 
+#ifndef VFGS_FAST_EXTRA_SMEM
+#define VFGS_FAST_EXTRA_SMEM 0 // unused bytes added to the launch (build-time knob: moves the L1/shared carveout)
+#endif
+// Shared-memory placement of the fast kernel's component images. pad = bytes between the start of the
+// kernel's dynamic shared memory and the next 32 KB boundary of the shared window, where the first LUT
+// goes: images are packed downwards from that boundary while they fit, the others upwards from the end of
+// the third LUT. served[c]: the fast kernel processes component c in this launch. Cr shares Cb's image
+// when both read the same pattern slot (fimg_bytes[2] = 0: nothing to copy).
+inline void place_fast_images(FgsParams& p, const TableInfo& bi, int pad, const bool served[3])
+{
+	int front = 0, back = 0;
+	for (int c = 0; c < 3; c++) {
+		p.fimg_bytes[c] = served[c] ? bi.fimg_bytes[c] : 0;
+		const int n = p.fimg_bytes[c];
+		p.fimg_off[c] = 0;
+		if (!n) continue;
+		if (c == 2 && p.fimg_bytes[1] && p.fimg_src[2] == p.fimg_src[1]) { // shares Cb's image: nothing to copy
+			p.fimg_off[2] = p.fimg_off[1]; p.fimg_bytes[2] = 0;
+			continue;
+		}
+		if (front + n <= pad) { front += n; p.fimg_off[c] = -front; }
+		else { p.fimg_off[c] = 3 * kLutBytes + back; back += n; }
+	}
+	p.fpad = pad;
+	p.fsmem = pad + 3 * kLutBytes + back + VFGS_FAST_EXTRA_SMEM;
+}
+
 // Which grain kernel serves which component of a whole-frame launch:
 //   fast    one pattern slot (no -128 byte), vector-aligned rows, width % 8 == 0        (fgs_fast.h)
 //   gather  several pattern slots (or a -128 byte), same alignment conditions, out of place (fgs_gather.h)
@@ -156,7 +196,7 @@ struct LaunchPlan {
 	int gather_smem; // dynamic shared memory of the gather launch
 };
 
-inline void plan_launches(const FgsParams& p, const TableInfo& bi, int mode, bool in_place, int smem_limit, LaunchPlan& lp)
+inline void plan_launches(const FgsParams& p, const TableInfo& bi, int mode, bool in_place, int smem_limit, int fast_pad, LaunchPlan& lp)
 {
 	lp.fast = lp.gather = lp.general = p;
 	lp.any_fast = lp.any_gather = lp.any_general = false;
@@ -170,6 +210,15 @@ inline void plan_launches(const FgsParams& p, const TableInfo& bi, int mode, boo
 			else if (!in_place) kind[c] = 1;
 		}
 		if (kind[c] == 1) ngather++;
+	}
+	{ // the fast kernel's tables must fit as well
+		bool served[3];
+		for (int c = 0; c < 3; c++) served[c] = kind[c] == 0;
+		place_fast_images(lp.fast, bi, fast_pad, served);
+		if (lp.fast.fsmem + 64 > smem_limit) {
+			for (int c = 0; c < 3; c++) if (kind[c] == 0) { kind[c] = 2; served[c] = false; }
+			place_fast_images(lp.fast, bi, fast_pad, served);
+		}
 	}
 	lp.gather_smem = kLutAlign + ngather * kLutBytes + bi.bytes;
 	if (ngather && lp.gather_smem > smem_limit) { // tables do not fit: those components take the general kernel
@@ -208,19 +257,20 @@ inline void plan_launches(const FgsParams& p, const TableInfo& bi, int mode, boo
 
 // What lfsr_states_kernel needs to turn a block register into a pattern-window offset (FgsParams::woffs).
 // Per component the entry has the format of the kernel that serves it:
-//   fast    offset inside the fast image of the +pattern / -pattern copy (block sign folded in) + oy * stride + ox
+//   fast    offset inside the fast image of the +pattern / -pattern copies (block sign folded in), there of the
+//           copy shifted by ox % 8, + oy * stride + ox rounded down to 8
 //   gather  oy * stride + ox inside a pattern slot, bit 15 set when the block sign is negative
 struct WoffParams {
 	int gather[3];
-	int off[3][2], stride[3], subx, suby;
+	int off[3][2], stride[3], copy[3], subx, suby; // copy: 0 for the gather format
 };
 inline WoffParams make_woff_params(const FgsParams& p, const int kind[3])
 {
 	WoffParams w;
 	for (int c = 0; c < 3; c++) {
 		w.gather[c] = kind[c] == 1;
-		if (w.gather[c]) { w.off[c][0] = 0; w.off[c][1] = 0x8000; w.stride[c] = p.pat_stride[c ? 1 : 0]; }
-		else { w.off[c][0] = p.fpat_off[c][0]; w.off[c][1] = p.fpat_off[c][1]; w.stride[c] = p.fpat_stride[c]; }
+		if (w.gather[c]) { w.off[c][0] = 0; w.off[c][1] = 0x8000; w.stride[c] = p.pat_stride[c ? 1 : 0]; w.copy[c] = 0; }
+		else { w.off[c][0] = p.fpat_off[c][0]; w.off[c][1] = p.fpat_off[c][1]; w.stride[c] = p.fpat_stride[c]; w.copy[c] = p.fpat_copy[c]; }
 	}
 	w.subx = p.subx; w.suby = p.suby;
 	return w;

@@ -316,7 +316,13 @@ def run_b200_arm(args):
             noise = torch.randint(-3, 4, (samples,), device="cuda", generator=gen)
             src[f * samples:(f + 1) * samples] = (base.to(torch.int32) + noise).clamp_(0, (1 << depth) - 1).to(sdt)
         del idx, base, noise
-    dst = torch.empty(F * samples, dtype=torch.int16 if (od or depth) > 8 else torch.uint8, device="cuda")
+    ddt = torch.int16 if (od or depth) > 8 else torch.uint8
+    if args.in_place and ddt == sdt:
+        dst = src  # diagnostic: the reference CLI's own mode (vfgs_main.c:664-682 adds grain in place)
+    else:
+        # --dst-offset (diagnostic): shifts the output pool relative to the input pool by a multiple of 256 bytes
+        pad = args.dst_offset // (2 if ddt == torch.int16 else 1)
+        dst = torch.empty(F * samples + pad, dtype=ddt, device="cuda")[pad:]
     stream = torch.cuda.current_stream()
 
     def step(s):
@@ -427,6 +433,8 @@ def main():
     ap.add_argument("--frames-per-step", type=int, default=0)
     ap.add_argument("--e2e-frames", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dst-offset", type=int, default=0, help="diagnostic: extra bytes (multiple of 256) in front of the output pool")
+    ap.add_argument("--in-place", action="store_true", help="diagnostic: output written over the input (same depth only)")
     ap.add_argument("--data", default="uniform", choices=["uniform", "natural"],
                     help="sample distribution of the synthetic frames (uniform random codes = worst case for the LUT/pattern gathers)")
     args = ap.parse_args()

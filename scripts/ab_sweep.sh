@@ -10,7 +10,7 @@ mkdir -p build/ab/libs
 cp $LIB build/ab/libs/cur.so
 for d in build/ab/*/; do
   n=$(basename $d); [ "$n" = libs ] && continue
-  nvcc $FLAGS $(cat $d/FLAGS 2>/dev/null) -o build/ab/libs/$n.so $d/versatilefilmgrain_b200/csrc/vfgs_b200.cu || echo "$n build failed"
+  eval "nvcc $FLAGS $(cat $d/FLAGS 2>/dev/null) -o build/ab/libs/$n.so $d/versatilefilmgrain_b200/csrc/vfgs_b200.cu" || echo "$n build failed"
 done
 for r in $(seq 1 ${ROUNDS:-2}); do
   for so in build/ab/libs/*.so; do

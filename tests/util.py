@@ -55,7 +55,10 @@ def build_emu() -> str:
     import subprocess
     here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu")
     so, src = os.path.join(here, "libemu.so"), os.path.join(here, "emu.cpp")
-    deps = [src] + [os.path.join(os.path.dirname(here), "..", "versatilefilmgrain_b200", "csrc", n) for n in ("fgs_task.h", "vfgs_core.h")]
+    csrc = os.path.join(os.path.dirname(here), "..", "versatilefilmgrain_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, n) for n in os.listdir(csrc) if n.endswith(".h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", so, src], check=True)
+        # -Bsymbolic: the inline functions of the shared headers must bind to this library's own copies, not to
+        # those libvfgs_b200.so exports when a test has loaded it first
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wl,-Bsymbolic", "-Wno-unknown-pragmas", "-o", so, src], check=True)
     return so

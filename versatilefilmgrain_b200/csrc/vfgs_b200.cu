@@ -240,7 +240,7 @@ int launch_apply(const FgsParams& p, cudaStream_t stream, KernelKind kind = kGen
 	if (kind == kFast) {
 		kern = p.in_bytes == 1 ? fgs_apply_fast_kernel<false, false>
 		     : p.out_bytes == 1 ? fgs_apply_fast_kernel<true, true> : fgs_apply_fast_kernel<true, false>;
-		threads = kFastThreads; smem = p.fsmem;
+		threads = fast_threads(p.in_bytes == 2, p.in_bytes == 2 && p.out_bytes == 1); smem = p.fsmem;
 		if (smem > c.fast_smem_attr) {
 			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_fast_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_fast_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -130,17 +130,25 @@ fgs_apply_kernel(const __grid_constant__ FgsParams p)
 // boundary of the shared window, expanded here from the 1 KB compact LUT in global memory) and the
 // components' +/- pattern copies, brought in by bulk async copies: in the gap between the start of dynamic
 // shared memory and the first LUT as far as they fit (FgsParams::fimg_off < 0), else behind the third LUT.
-#ifndef VFGS_FAST_THREADS
-#define VFGS_FAST_THREADS 1024
-#define VFGS_FAST_CTAS 1
+// CTA size per variant, measured on B200 (scripts/ab_sweep.sh, same box, 4K/8K/1080p): the 8-bit-output kernel
+// is bound by instruction issue and the shared-memory pipe and wants all 32 warps; the 16-bit-output kernel is
+// HBM-bound with equal read and write streams and peaks at 24 warps x 4 lines in flight per lane (more
+// outstanding lines per SM lower the DRAM efficiency again: 768 threads 95.6 %, 1024 threads 89 % of the
+// measured copy bandwidth at 4K).
+#ifndef VFGS_FAST_THREADS8
+#define VFGS_FAST_THREADS8 1024  // 16-bit in, 8-bit out
 #endif
-constexpr int kFastThreads = VFGS_FAST_THREADS; // build-time knobs for experiments
-constexpr int kFastWarps = kFastThreads / 32;
+#ifndef VFGS_FAST_THREADS16
+#define VFGS_FAST_THREADS16 768  // 16-bit out (and 8-bit in, 8-bit out)
+#endif
+template <bool IN16, bool OUT8> struct FastCta { static constexpr int threads = (IN16 && OUT8) ? VFGS_FAST_THREADS8 : VFGS_FAST_THREADS16; };
+inline int fast_threads(bool in16, bool out8) { return (in16 && out8) ? VFGS_FAST_THREADS8 : VFGS_FAST_THREADS16; }
 
 template <bool IN16, bool OUT8>
-__global__ void __launch_bounds__(kFastThreads, VFGS_FAST_CTAS)
+__global__ void __launch_bounds__(FastCta<IN16, OUT8>::threads, 1)
 fgs_apply_fast_kernel(const __grid_constant__ FgsParams p)
 {
+	constexpr int kFastThreads = FastCta<IN16, OUT8>::threads, kFastWarps = kFastThreads / 32;
 	extern __shared__ __align__(128) uint8_t smem[];
 	__shared__ __align__(8) uint64_t bar;
 

@@ -8,6 +8,10 @@
 
 #include "fgs_gather.h"
 
+#ifndef VFGS_FAST_ROW_SKEW
+#define VFGS_FAST_ROW_SKEW 8 // bytes, multiple of 8 (build-time knob for experiments)
+#endif
+
 namespace vfgs {
 
 constexpr int kSlots = 9; // 8 settable + the always-zero slot 8 (vfgs_hw.c:49)
@@ -86,12 +90,15 @@ inline void build_tables(const HwState& h, TableInfo& g_bi, std::vector<uint8_t>
 			for (int x = 0; x < cols; x++)
 				if (h.pattern[c ? 1 : 0][slot][r][x] == -128) { ok = false; break; }
 		g_bi.fast_ok[c] = ok;
-		g_bi.fpat_stride[c] = cols;
-		g_bi.fpat_copy[c] = rows * cols;
+		// row pitch = cols + VFGS_FAST_ROW_SKEW: the window rows oy are multiples of 4 (or 2), so with a power-of-two
+		// pitch every window of a line would start in the same few banks; the skew spreads them over all banks
+		const int pitch = cols + VFGS_FAST_ROW_SKEW;
+		g_bi.fpat_stride[c] = pitch;
+		g_bi.fpat_copy[c] = rows * pitch;
 		g_bi.fpat_off[c][0] = 0;
-		g_bi.fpat_off[c][1] = ncopy * rows * cols;
+		g_bi.fpat_off[c][1] = ncopy * rows * pitch;
 		g_bi.fimg_src[c] = off;
-		g_bi.fimg_bytes[c] = ok ? 2 * ncopy * rows * cols : 0;
+		g_bi.fimg_bytes[c] = ok ? 2 * ncopy * rows * pitch : 0;
 		if (c == 2 && ok && g_bi.fast_ok[1] && g_bi.uniform_pi[1] == slot) g_bi.fimg_src[2] = g_bi.fimg_src[1]; // Cb and Cr read the same slot: one image
 		else off += g_bi.fimg_bytes[c];
 	}
@@ -104,12 +111,13 @@ inline void build_tables(const HwState& h, TableInfo& g_bi, std::vector<uint8_t>
 		const int rows = c ? crows : 64, cols = c ? ccols : 64;
 		const int ncopy = fast_copies((c && h.csubx > 1) ? 8 : 16), shift = 8 / ncopy;
 		for (int k = 0; k < ncopy; k++) {
-			int8_t* plus = (int8_t*)&g_fblob[g_bi.fimg_src[c] + g_bi.fpat_off[c][0] + k * rows * cols];
-			int8_t* minus = (int8_t*)&g_fblob[g_bi.fimg_src[c] + g_bi.fpat_off[c][1] + k * rows * cols];
+			const int pitch = g_bi.fpat_stride[c];
+			int8_t* plus = (int8_t*)&g_fblob[g_bi.fimg_src[c] + g_bi.fpat_off[c][0] + k * g_bi.fpat_copy[c]];
+			int8_t* minus = (int8_t*)&g_fblob[g_bi.fimg_src[c] + g_bi.fpat_off[c][1] + k * g_bi.fpat_copy[c]];
 			for (int r = 0; r < rows; r++)
 				for (int x = 0; x + k * shift < cols; x++) {
 					const int8_t v = h.pattern[c ? 1 : 0][g_bi.uniform_pi[c]][r][x + k * shift];
-					plus[r * cols + x] = v; minus[r * cols + x] = (int8_t)-v;
+					plus[r * pitch + x] = v; minus[r * pitch + x] = (int8_t)-v;
 				}
 		}
 	}

@@ -380,6 +380,29 @@ def run_b200_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * Fe * e2e_steps / float(t.item())
 
+    # the box's PCIe ceiling for the same bytes: this step's H2D and D2H copies alone, concurrently on two
+    # streams from the same pinned buffers, all ranks at once, no kernels
+    d_in, d_out = torch.empty_like(h_in, device="cuda"), torch.empty_like(h_out, device="cuda")
+    s_up, s_down = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def copies():
+        with torch.cuda.stream(s_up):
+            d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s_down):
+            h_out.copy_(d_out, non_blocking=True)
+
+    copies()
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(e2e_steps):
+        copies()
+    torch.cuda.synchronize()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    copy_only_value = world * Fe * e2e_steps / float(t.item())
+    del d_in, d_out
+
     peak, peak_src = measured_peak_gbs()
     traffic = traffic_src = None
     try:  # DRAM bytes per frame of the grain kernel from the committed ncu capture of this workload
@@ -400,7 +423,10 @@ def run_b200_arm(args):
         "config": workload_config(args.workload, F, f"inputs larger than L2: resident pool {F * (in_bytes + out_bytes) / 1e9:.1f} GB per GPU streamed once per step"),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": Fe * in_bytes, "d2h_bytes_per_step": Fe * out_bytes,
-                "frames_per_step": Fe, "steps": e2e_steps, "host_buffers": "pinned", "cpu_placement": placement},
+                "frames_per_step": Fe, "steps": e2e_steps, "host_buffers": "pinned", "cpu_placement": placement,
+                "gbs_each_way": [e2e_value * in_bytes / 1e9, e2e_value * out_bytes / 1e9],
+                "pcie_copies_alone": {"value": copy_only_value, "unit": UNIT,
+                                      "what": "the same H2D and D2H copies without kernels, concurrently, all ranks: the box's PCIe ceiling for this step"}},
         "gpu_launches": int(gpu_launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,

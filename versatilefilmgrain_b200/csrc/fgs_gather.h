@@ -111,6 +111,23 @@ VFGS_HD void neighbour_samples(const uint32_t raw[4], int lane, uint32_t gl, uin
 	vl = gl; vr = gr;
 #endif
 }
+// 16-sample blocks: a lane is the first or the second half of a block and has one block edge, so one
+// neighbour sample serves. First halves (even lanes) take the last sample of the lane to their left, second
+// halves the first sample of the lane to their right: one shuffle, every lane sending what its receiver needs.
+template <bool IN16>
+VFGS_HD uint32_t neighbour_sample(const uint32_t raw[4], int lane, uint32_t gmem, bool second_half, bool right_in_picture)
+{
+#if defined(__CUDA_ARCH__)
+	const uint32_t first = IN16 ? raw[0] & 0xffffu : raw[0] & 0xffu;
+	const uint32_t last = IN16 ? raw[3] >> 16 : raw[1] >> 24;
+	const uint32_t got = __shfl_sync(0xffffffffu, second_half ? last : first, second_half ? lane + 1 : lane - 1);
+	if (second_half) return !right_in_picture ? 0u : lane == 31 ? gmem : got;
+	return lane == 0 ? gmem : got;
+#else
+	(void)raw; (void)lane;
+	return (second_half && !right_in_picture) ? 0u : gmem;
+#endif
+}
 
 // LUT index bits (intensity * 128) of sample e of a lane's raw words.
 template <bool IN16, int E>
@@ -140,7 +157,8 @@ VFGS_HD void gather_sample(const GatherLane& L, const GatherUp& U, uint32_t ibit
 	grain = g;
 }
 
-template <bool IN16, bool OUT8>
+// MERGE (16-sample blocks): the lane's one neighbour sample is vl, its window L.lh / U.lh and sign L.s_l / U.s_l.
+template <bool IN16, bool OUT8, bool MERGE>
 VFGS_HD void gather_line(const GatherLane& L, const GatherUp& U, int rc, int w_cur, int w_up, int ru, int in_shift,
                          const uint32_t raw[4], uint32_t vl, uint32_t vr, uint32_t outw[4])
 {
@@ -158,7 +176,16 @@ VFGS_HD void gather_line(const GatherLane& L, const GatherUp& U, int rc, int w_c
 	// neighbours' edge samples (their own intensity selects their pattern slot), then the edge filter
 	// (vfgs_hw.c:250-259). Computed unconditionally with harmless addresses when there is no neighbour
 	// (lh/rh fall back to the lane's own window) and selected at the end: straight-line code, no branches.
-	{
+	if (MERGE) {
+		const smem_addr_t offn = (smem_addr_t)(lds32(L.lut | (smem_addr_t)(((vl >> in_shift) & 0xffu) << 7)) >> 8);
+		int h = lds_s8(L.lh + rc + offn);
+		if (w_cur) h = (h * (w_cur * L.s_l) + lds_s8(U.lh + ru + offn) * (w_up * U.s_l) + 16) >> 5;
+		else h *= L.s_l;
+		const int a = L.has_right ? g[7] : g[0], b = L.has_right ? g[6] : g[1];
+		const int f = (h + 3 * a + b + 2) >> 2; // taps read unfiltered neighbours
+		g[0] = L.has_left ? f : g[0];
+		g[7] = L.has_right ? f : g[7];
+	} else {
 		const smem_addr_t offl = (smem_addr_t)(lds32(L.lut | (smem_addr_t)(((vl >> in_shift) & 0xffu) << 7)) >> 8);
 		const smem_addr_t offr = (smem_addr_t)(lds32(L.lut | (smem_addr_t)(((vr >> in_shift) & 0xffu) << 7)) >> 8);
 		int hl = lds_s8(L.lh + rc + offl), hr = lds_s8(L.rh + rc + offr);
@@ -175,18 +202,19 @@ VFGS_HD void gather_line(const GatherLane& L, const GatherUp& U, int rc, int w_c
 	}
 
 	if (IN16) {
+		constexpr int kRound = OUT8 ? 0x28000 : 0x8000; // 8-bit output: the + 2 of yuv.c:231 rides on the rounding and the clip range (fast_line)
 		uint32_t r[4];
 #pragma unroll
 		for (int k = 0; k < 4; k++) {
-			const int a_lo = sc[2 * k] * (g[2 * k] * L.pow16) + 0x8000;
-			const int a_hi = sc[2 * k + 1] * (g[2 * k + 1] * L.pow16) + 0x8000;
+			const int a_lo = sc[2 * k] * (g[2 * k] * L.pow16) + kRound;
+			const int a_hi = sc[2 * k + 1] * (g[2 * k + 1] * L.pow16) + kRound;
 			const uint32_t d2 = prmt((uint32_t)a_lo, (uint32_t)a_hi, 0x7632);
 			const uint32_t v2 = min_u16x2(raw[k], 0x3fff3fffu);
 			r[k] = min_s16x2(add_max_s16x2(v2, d2, L.lo2), L.hi2);
 		}
 		if (OUT8) {
 #pragma unroll
-			for (int k = 0; k < 4; k++) r[k] = ((r[k] + 0x00020002u) >> 2) & 0x00ff00ffu;
+			for (int k = 0; k < 4; k++) r[k] >>= 2;
 			outw[0] = prmt(r[0], r[1], 0x6420);
 			outw[1] = prmt(r[2], r[3], 0x6420);
 		} else {
@@ -215,15 +243,14 @@ VFGS_HD smem_addr_t gather_window(smem_addr_t bank, uint32_t entry, int col, int
 	return bank + (smem_addr_t)((entry & 0x7fffu) + (uint32_t)col);
 }
 
-template <bool IN16, bool OUT8>
-VFGS_HD void process_task_gather(const FgsParams& p, smem_addr_t luts, smem_addr_t img, uint32_t task, int lane)
+template <bool IN16, bool OUT8, int NSH>
+VFGS_HD void gather_task_body(const FgsParams& p, smem_addr_t luts, smem_addr_t img, const TaskGeom& t, int lane)
 {
-	const TaskGeom t = decode_task(p, task);
+	constexpr bool MERGE = NSH == 4; // one block edge per lane
 	const int c = t.c;
 	const Plane& pl = p.comp[c];
 	const int ysh = (c && p.suby > 1) ? 1 : 0;
-	const int nsh = (c && p.subx > 1) ? 3 : 4;
-	const int n = 1 << nsh;
+	constexpr int n = 1 << NSH;
 	const int k0 = t.seg * kSegSamples + lane * kSamplesPerLane;
 	// lanes right of the picture stay in the loop (the neighbour exchange is a warp shuffle) but
 	// neither load nor store
@@ -240,18 +267,20 @@ VFGS_HD void process_task_gather(const FgsParams& p, smem_addr_t luts, smem_addr
 	const uint8_t* src = pl.in + (long long)t.f * p.in_frame_bytes + (long long)cl0 * in_pitch + (long long)k0 * IB;
 	uint8_t* dst = pl.out + (long long)t.f * p.out_frame_bytes + (long long)cl0 * out_pitch + (long long)k0 * OB;
 
-	const int b = active ? (k0 >> nsh) : 0; // idle lanes must not index past the register row
+	const int b = active ? (k0 >> NSH) : 0; // idle lanes must not index past the register row
 	const int i0 = k0 & (n - 1);
 	GatherLane L;
 	L.has_left = active && (i0 == 0) && (b > 0);
 	L.has_right = active && (i0 + kSamplesPerLane == n) && (b + 1 < p.nb);
+	const bool second_half = i0 != 0; // MERGE only
 	const bool right_in_picture = k0 + kSamplesPerLane < pl.width; // samples right of the picture read as 0
 	// who fetches a neighbour sample from memory: every lane in the host build, the warp's end lanes on the device
 	const bool mem_left = L.has_left && (kHaloFromMemory || lane == 0);
 	const bool mem_right = L.has_right && right_in_picture && (kHaloFromMemory || lane == 31);
 
-	uint32_t raw[kFastLB][4] = {}, vl[kFastLB], vr[kFastLB]; // vl/vr: neighbour samples fetched from memory (kept apart:
-	                                                          // combining them would wait for the loads just issued)
+	// vl/vr: neighbour samples fetched from memory (kept apart from raw: combining them would wait for the loads
+	// just issued); MERGE keeps the lane's one neighbour in vl
+	uint32_t raw[kFastLB][4] = {}, vl[kFastLB], vr[kFastLB];
 #pragma unroll
 	for (int q = 0; q < kFastLB; q++) {
 		const uint8_t* row = src + (q < nl ? q : nl - 1) * in_pitch;
@@ -259,15 +288,21 @@ VFGS_HD void process_task_gather(const FgsParams& p, smem_addr_t luts, smem_addr
 			if (IN16) ld_global_16(row, raw[q]);
 			else ld_global_8(row, raw[q]);
 		}
-		vl[q] = ld_sample_if<IB>(row - IB, mem_left);
-		vr[q] = ld_sample_if<IB>(row + kSamplesPerLane * IB, mem_right);
+		if (MERGE) {
+			vl[q] = ld_sample_if<IB>(second_half ? row + kSamplesPerLane * IB : row - IB, mem_left || mem_right);
+			vr[q] = 0;
+		} else {
+			vl[q] = ld_sample_if<IB>(row - IB, mem_left);
+			vr[q] = ld_sample_if<IB>(row + kSamplesPerLane * IB, mem_right);
+		}
 	}
 
 	const int bank = c ? 1 : 0;
 	L.stride = p.pat_stride[bank];
 	L.lut = luts + (smem_addr_t)(p.glut_index[c] * kLutBytes + lane * 4);
 	L.pow16 = p.pow16;
-	L.lo2 = (uint32_t)p.lo[c] * 0x00010001u; L.hi2 = (uint32_t)p.hi[c] * 0x00010001u;
+	constexpr int kOutBias = (IN16 && OUT8) ? 2 : 0;
+	L.lo2 = (uint32_t)(p.lo[c] + kOutBias) * 0x00010001u; L.hi2 = (uint32_t)(p.hi[c] + kOutBias) * 0x00010001u;
 
 	const int srow = t.r - p.stream_row0;
 	const uint16_t* w_cur = p.woffs + (((long long)t.f * p.stream_rows + srow) * p.spitch + 1 + b) * 4 + c;
@@ -275,7 +310,7 @@ VFGS_HD void process_task_gather(const FgsParams& p, smem_addr_t luts, smem_addr
 	L.own = gather_window(bank_addr, w_cur[0], i0, L.s_own);
 	L.lh = L.rh = L.own; L.s_l = L.s_r = 1;
 	if (L.has_left) L.lh = gather_window(bank_addr, w_cur[-4], n - 1, L.s_l);
-	if (L.has_right) L.rh = gather_window(bank_addr, w_cur[4], 0, L.s_r);
+	if (L.has_right) (MERGE ? L.lh : L.rh) = gather_window(bank_addr, w_cur[4], 0, MERGE ? L.s_l : L.s_r);
 
 	GatherUp U;
 	U.own = U.lh = U.rh = L.own; U.s_own = U.s_l = U.s_r = 1;
@@ -284,7 +319,7 @@ VFGS_HD void process_task_gather(const FgsParams& p, smem_addr_t luts, smem_addr
 		const uint16_t* w_up = w_cur - p.spitch * 4;
 		U.own = gather_window(bank_addr, w_up[0], i0, U.s_own);
 		if (L.has_left) U.lh = gather_window(bank_addr, w_up[-4], n - 1, U.s_l);
-		if (L.has_right) U.rh = gather_window(bank_addr, w_up[4], 0, U.s_r);
+		if (L.has_right) (MERGE ? U.lh : U.rh) = gather_window(bank_addr, w_up[4], 0, MERGE ? U.s_l : U.s_r);
 	}
 
 	int rc = 0;
@@ -298,14 +333,19 @@ VFGS_HD void process_task_gather(const FgsParams& p, smem_addr_t luts, smem_addr
 			int w_cur = 0, w_up = 0, ru = 0;
 			if (q == 0 && ovl) { w_cur = ysh ? 20 : 12; w_up = ysh ? 20 : 24; ru = (16 >> ysh) * L.stride; }
 			if (q == 1 && ovl && !ysh) { w_cur = 24; w_up = 12; ru = 17 * L.stride; }
-			uint32_t nl_s, nr_s;
-			neighbour_samples<IN16>(raw[q], lane, vl[q], vr[q], right_in_picture, nl_s, nr_s);
-			gather_line<IN16, OUT8>(L, U, rc, w_cur, w_up, ru, p.bs, raw[q], nl_s, nr_s, w);
+			uint32_t nl_s, nr_s = 0;
+			if (MERGE) nl_s = neighbour_sample<IN16>(raw[q], lane, vl[q], second_half, right_in_picture);
+			else neighbour_samples<IN16>(raw[q], lane, vl[q], vr[q], right_in_picture, nl_s, nr_s);
+			gather_line<IN16, OUT8, MERGE>(L, U, rc, w_cur, w_up, ru, p.bs, raw[q], nl_s, nr_s, w);
 			const bool more = line + kFastLB < nl;
 			if (IN16) ld_global_16_if(nxt, raw[q], more && active);
 			else ld_global_8_if(nxt, raw[q], more && active);
-			vl[q] = ld_sample_if<IB>(nxt - IB, mem_left && more);
-			vr[q] = ld_sample_if<IB>(nxt + kSamplesPerLane * IB, mem_right && more);
+			if (MERGE) {
+				vl[q] = ld_sample_if<IB>(second_half ? nxt + kSamplesPerLane * IB : nxt - IB, (mem_left || mem_right) && more);
+			} else {
+				vl[q] = ld_sample_if<IB>(nxt - IB, mem_left && more);
+				vr[q] = ld_sample_if<IB>(nxt + kSamplesPerLane * IB, mem_right && more);
+			}
 			if (line < nl && active) {
 				if (OB == 2) st_global_16(dst, w);
 				else st_global_8(dst, w);
@@ -314,6 +354,16 @@ VFGS_HD void process_task_gather(const FgsParams& p, smem_addr_t luts, smem_addr
 		}
 		ovl = false;
 	}
+}
+
+// Dispatch on the component's block size (16 samples: luma and non-subsampled chroma; 8: chroma
+// subsampled horizontally).
+template <bool IN16, bool OUT8>
+VFGS_HD void process_task_gather(const FgsParams& p, smem_addr_t luts, smem_addr_t img, uint32_t task, int lane)
+{
+	const TaskGeom t = decode_task(p, task);
+	if (t.c && p.subx > 1) gather_task_body<IN16, OUT8, 3>(p, luts, img, t, lane);
+	else gather_task_body<IN16, OUT8, 4>(p, luts, img, t, lane);
 }
 
 } // namespace vfgs

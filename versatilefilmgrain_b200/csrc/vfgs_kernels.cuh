@@ -178,11 +178,16 @@ fgs_apply_fast_kernel(const __grid_constant__ FgsParams p)
 // Gather path: components with sample-adaptive pattern selection (fgs_gather.h). Shared memory: one
 // per-lane replicated LUT (32 KB, entry = scale | slot byte offset << 8) per gather component, each on a
 // 32 KB boundary, then the general table image (compact LUTs + pattern slots) brought in by one bulk copy.
-constexpr int kGatherThreads = 384; // 2 CTAs per SM at up to 80 registers: the gather path carries more per-lane state
+#ifndef VFGS_GATHER_THREADS
+#define VFGS_GATHER_THREADS 768
+#define VFGS_GATHER_CTAS 1
+#endif
+constexpr int kGatherThreads = VFGS_GATHER_THREADS; // one CTA per SM at up to 80 registers (the gather path carries more per-lane state);
+                                                    // measured ahead of 2 x 384 (one table image per SM) and of 640/704/832 threads
 constexpr int kGatherWarps = kGatherThreads / 32;
 
 template <bool IN16, bool OUT8>
-__global__ void __launch_bounds__(kGatherThreads, 2)
+__global__ void __launch_bounds__(kGatherThreads, VFGS_GATHER_CTAS)
 fgs_apply_gather_kernel(const __grid_constant__ FgsParams p)
 {
 	extern __shared__ __align__(128) uint8_t smem[];

@@ -8,6 +8,9 @@
 
 #include "fgs_gather.h"
 
+#ifndef VFGS_PAT_ROW_SKEW
+#define VFGS_PAT_ROW_SKEW 8 // bytes (general image: gather and general kernels; build-time knob for experiments)
+#endif
 #ifndef VFGS_FAST_ROW_SKEW
 #define VFGS_FAST_ROW_SKEW 8 // bytes, multiple of 8 (build-time knob for experiments)
 #endif
@@ -48,7 +51,8 @@ struct TableInfo {
 };
 
 // General image layout (all offsets multiples of 16): LUT uint16[3][256] = scale | slot << 8, then the
-// luma slots in use (4096 B each), then the chroma slots in use packed to (64/csuby) rows x (64/csubx) bytes.
+// luma slots in use (64 rows), then the chroma slots in use packed to (64/csuby) rows x (64/csubx) bytes;
+// rows cols + VFGS_PAT_ROW_SKEW bytes apart.
 inline void build_tables(const HwState& h, TableInfo& g_bi, std::vector<uint8_t>& g_blob, std::vector<uint8_t>& g_fblob)
 {
 	int nslot[2] = {1, 1};
@@ -62,20 +66,25 @@ inline void build_tables(const HwState& h, TableInfo& g_bi, std::vector<uint8_t>
 		g_bi.uniform_pi[c] = uni;
 	}
 	const int crows = 64 / h.csuby, ccols = 64 / h.csubx;
+	// pattern rows are stored cols + VFGS_PAT_ROW_SKEW bytes apart: the window rows are multiples of 4 (or 2), so
+	// with the natural power-of-two pitch the byte gathers of a line would fall into half of the banks
+	const int lpitch = 64 + VFGS_PAT_ROW_SKEW, cpitch = ccols + VFGS_PAT_ROW_SKEW;
 	g_bi.lut_off = 0;
 	g_bi.pat_off[0] = 3 * 256 * 2;
-	g_bi.pat_size[0] = 64 * 64; g_bi.pat_stride[0] = 64;
-	g_bi.pat_off[1] = g_bi.pat_off[0] + nslot[0] * 4096;
-	g_bi.pat_size[1] = crows * ccols; g_bi.pat_stride[1] = ccols;
+	g_bi.pat_size[0] = 64 * lpitch; g_bi.pat_stride[0] = lpitch;
+	g_bi.pat_off[1] = g_bi.pat_off[0] + nslot[0] * g_bi.pat_size[0];
+	g_bi.pat_size[1] = crows * cpitch; g_bi.pat_stride[1] = cpitch;
 	g_bi.bytes = (g_bi.pat_off[1] + nslot[1] * g_bi.pat_size[1] + 16 + 15) & ~15; // +16: fetch8 may touch one word past an octet
 	g_blob.assign((size_t)g_bi.bytes, 0);
 	uint16_t* lut = (uint16_t*)g_blob.data();
 	for (int c = 0; c < 3; c++)
 		for (int i = 0; i < 256; i++) lut[c * 256 + i] = (uint16_t)(h.slut[c][i] | ((h.plut[c][i] >> 4) << 8));
-	for (int s = 0; s < nslot[0]; s++) memcpy(&g_blob[g_bi.pat_off[0] + s * 4096], h.pattern[0][s], 4096);
+	for (int s = 0; s < nslot[0]; s++)
+		for (int r = 0; r < 64; r++)
+			memcpy(&g_blob[g_bi.pat_off[0] + s * g_bi.pat_size[0] + r * lpitch], h.pattern[0][s][r], 64);
 	for (int s = 0; s < nslot[1]; s++)
 		for (int r = 0; r < crows; r++)
-			memcpy(&g_blob[g_bi.pat_off[1] + s * g_bi.pat_size[1] + r * ccols], h.pattern[1][s][r], (size_t)ccols);
+			memcpy(&g_blob[g_bi.pat_off[1] + s * g_bi.pat_size[1] + r * cpitch], h.pattern[1][s][r], (size_t)ccols);
 
 	// fast-path image: compact scale LUT, then per component the single slot as +pattern and -pattern, each in
 	// fast_copies() column-shifted copies (copy k holds the pattern moved left by k * 8 / copies bytes), so that

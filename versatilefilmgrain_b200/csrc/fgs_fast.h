@@ -209,9 +209,11 @@ VFGS_HD void octet(smem_addr_t a, uint32_t& w0, uint32_t& w1)
 // Measured on B200 (scripts/ab_sweep.sh, same box): the merged form is +3 points of HBM roofline for the
 // issue-bound 8-bit-output kernel and -4 points for the HBM-bound 16-bit-output kernel, hence mode 2.
 #ifndef VFGS_FAST_MERGE_HALO
-#define VFGS_FAST_MERGE_HALO 2 // 0 never, 1 always, 2 only with 8-bit output
+#define VFGS_FAST_MERGE_HALO 2 // 0 never, 1 always, 2 only with 8-bit output or input
 #endif
-template <bool OUT8> struct MergeHalo { static constexpr bool value = VFGS_FAST_MERGE_HALO == 1 || (VFGS_FAST_MERGE_HALO == 2 && OUT8); };
+template <bool IN16, bool OUT8> struct MergeHalo { // mode 2: the issue-bound variants (8-bit output, 8-bit input)
+	static constexpr bool value = VFGS_FAST_MERGE_HALO == 1 || (VFGS_FAST_MERGE_HALO == 2 && (OUT8 || !IN16));
+};
 struct FastLane {
 	smem_addr_t own;         // the lane's octet, pattern row of line j = 0 of the current block
 	smem_addr_t lh, rh;      // halo bytes: last column of block b-1 / first column of block b+1
@@ -244,7 +246,7 @@ VFGS_HD void fast_line(const FastLane& L, int rc, int w_cur, int w_up, const Fas
 	int g[8];
 	g[0] = octet_byte<0>(c0, c1); g[1] = octet_byte<1>(c0, c1); g[2] = octet_byte<2>(c0, c1); g[3] = octet_byte<3>(c0, c1);
 	g[4] = octet_byte<4>(c0, c1); g[5] = octet_byte<5>(c0, c1); g[6] = octet_byte<6>(c0, c1); g[7] = octet_byte<7>(c0, c1);
-	if (MergeHalo<OUT8>::value && NSH == 4) {
+	if (MergeHalo<IN16, OUT8>::value && NSH == 4) {
 		// one edge per lane: halo h next to a, then b (left edge: h | g0 g1, right edge: g6 g7 | h mirrored)
 		const bool edge = L.has_left || L.has_right;
 		int h = edge ? lds_s8(L.lh + rc) : 0;
@@ -309,21 +311,20 @@ VFGS_HD void fast_line(const FastLane& L, int rc, int w_cur, int w_up, const Fas
 			outw[0] = r[0]; outw[1] = r[1]; outw[2] = r[2]; outw[3] = r[3];
 		}
 	} else {
-		const int lo = (int)(L.lo2 & 0xffff), hi = (int)(L.hi2 & 0xffff);
-		int o[8];
+		// 8-bit samples: widened two at a time into the 16x2 form of the 16-bit path (no cap needed: v <= 255)
+		uint32_t r[4];
 #pragma unroll
-		for (int e = 0; e < 8; e++) {
-			const uint32_t word = raw[e >> 2];
-			const int sh = (e & 3) * 8;
-			const int v = (int)((word >> sh) & 0xff);
-			const uint32_t ibits = sh >= 7 ? (word >> (sh - 7)) & 0x7f80u : (word << (7 - sh)) & 0x7f80u; // v * 128
-			const int s = (int)lds32(L.lut | (smem_addr_t)ibits);
-			int x = v + ((s * g[e] + 0x8000) >> 16);
-			x = x > hi ? hi : x;
-			o[e] = x < lo ? lo : x;
+		for (int k = 0; k < 4; k++) {
+			const uint32_t v2 = prmt(raw[k >> 1], 0u, (k & 1) ? 0x4342 : 0x4140); // bytes 2k', 2k'+1 of the word, zero-extended
+			const int s_lo = (int)lds32(L.lut | (smem_addr_t)((v2 << 7) & 0x7f80u));  // LUT index = sample (vfgs_hw.c:211), times 128
+			const int s_hi = (int)lds32(L.lut | (smem_addr_t)((v2 >> 9) & 0x7f80u));
+			const int a_lo = s_lo * g[2 * k] + 0x8000;
+			const int a_hi = s_hi * g[2 * k + 1] + 0x8000;
+			const uint32_t d2 = prmt((uint32_t)a_lo, (uint32_t)a_hi, 0x7632);
+			r[k] = min_s16x2(add_max_s16x2(v2, d2, L.lo2), L.hi2);  // vfgs_hw.c:267
 		}
-		outw[0] = (uint32_t)o[0] | ((uint32_t)o[1] << 8) | ((uint32_t)o[2] << 16) | ((uint32_t)o[3] << 24);
-		outw[1] = (uint32_t)o[4] | ((uint32_t)o[5] << 8) | ((uint32_t)o[6] << 16) | ((uint32_t)o[7] << 24);
+		outw[0] = prmt(r[0], r[1], 0x6420);
+		outw[1] = prmt(r[2], r[3], 0x6420);
 	}
 }
 
@@ -405,7 +406,7 @@ VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, const TaskGeom&
 	L.own = img + (smem_addr_t)(w_cur[0] + i0);
 	L.lh = L.rh = L.own;
 	if (L.has_left) L.lh = img + (smem_addr_t)(w_cur[-4] + n - 1);
-	if (L.has_right) (MergeHalo<OUT8>::value && NSH == 4 ? L.lh : L.rh) = img + (smem_addr_t)w_cur[4];
+	if (L.has_right) (MergeHalo<IN16, OUT8>::value && NSH == 4 ? L.lh : L.rh) = img + (smem_addr_t)w_cur[4];
 
 	// the first lines of a stripe overlap the block-row above (never in the first stripe, y <= 15)
 	FastUp U;
@@ -415,7 +416,7 @@ VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, const TaskGeom&
 		const uint16_t* w_up = w_cur - p.spitch * 4;
 		U.own = img + (smem_addr_t)(w_up[0] + i0);
 		if (L.has_left) U.lh = img + (smem_addr_t)(w_up[-4] + n - 1);
-		if (L.has_right) (MergeHalo<OUT8>::value && NSH == 4 ? U.lh : U.rh) = img + (smem_addr_t)w_up[4];
+		if (L.has_right) (MergeHalo<IN16, OUT8>::value && NSH == 4 ? U.lh : U.rh) = img + (smem_addr_t)w_up[4];
 	}
 
 	int rc = 0;

@@ -143,60 +143,79 @@ VFGS_HD uint32_t index_bits(const uint32_t raw[4])
 	}
 }
 
-// entry -> scale and signed grain of one sample (column E of the lane's window)
+// entry -> scale and grain byte of one sample (column E of the lane's window); the block's sign is not applied
 template <int E>
-VFGS_HD void gather_sample(const GatherLane& L, const GatherUp& U, uint32_t ibits, int rc, int wc_s, int wu_s, int ru,
-                           int& scale, int& grain)
+VFGS_HD void gather_sample(const GatherLane& L, uint32_t ibits, int rc, int& scale, int& grain)
 {
 	const uint32_t ent = lds32(L.lut | (smem_addr_t)ibits);
 	scale = (int)(ent & 0xff);
-	const smem_addr_t off = (smem_addr_t)(ent >> 8) + E;
-	int g = lds_s8(L.own + rc + off);
-	if (wu_s == 0 && wc_s == 0) g *= L.s_own;
-	else g = (g * wc_s + lds_s8(U.own + ru + off) * wu_s + 16) >> 5; // weights carry the two block signs
-	grain = g;
+	grain = lds_s8(L.own + rc + (smem_addr_t)(ent >> 8) + E);
+}
+// the same sample's byte in the window of the block above, blended in (vfgs_hw.c:223-229); the weights carry
+// the two block signs, so the result is fully signed
+template <int E>
+VFGS_HD int gather_blend(const GatherLane& L, const GatherUp& U, uint32_t ibits, int ru, int wc_s, int wu_s, int g)
+{
+	const smem_addr_t off = (smem_addr_t)(lds32(L.lut | (smem_addr_t)ibits) >> 8) + E; // looked up again: overlap lines only
+	return (g * wc_s + lds_s8(U.own + ru + off) * wu_s + 16) >> 5;
 }
 
 // MERGE (16-sample blocks): the lane's one neighbour sample is vl, its window L.lh / U.lh and sign L.s_l / U.s_l.
+// On lines without vertical overlap g[] stays free of the block's sign until the scale multiply (the sign rides
+// on the 2^(16 - shift) factor); only the edge filter, whose neighbour tap carries another block's sign, applies
+// it explicitly.
 template <bool IN16, bool OUT8, bool MERGE>
 VFGS_HD void gather_line(const GatherLane& L, const GatherUp& U, int rc, int w_cur, int w_up, int ru, int in_shift,
                          const uint32_t raw[4], uint32_t vl, uint32_t vr, uint32_t outw[4])
 {
-	const int wc_s = w_cur * L.s_own, wu_s = w_up * U.s_own;
 	int g[8], sc[8];
-	gather_sample<0>(L, U, index_bits<IN16, 0>(raw), rc, wc_s, wu_s, ru, sc[0], g[0]);
-	gather_sample<1>(L, U, index_bits<IN16, 1>(raw), rc, wc_s, wu_s, ru, sc[1], g[1]);
-	gather_sample<2>(L, U, index_bits<IN16, 2>(raw), rc, wc_s, wu_s, ru, sc[2], g[2]);
-	gather_sample<3>(L, U, index_bits<IN16, 3>(raw), rc, wc_s, wu_s, ru, sc[3], g[3]);
-	gather_sample<4>(L, U, index_bits<IN16, 4>(raw), rc, wc_s, wu_s, ru, sc[4], g[4]);
-	gather_sample<5>(L, U, index_bits<IN16, 5>(raw), rc, wc_s, wu_s, ru, sc[5], g[5]);
-	gather_sample<6>(L, U, index_bits<IN16, 6>(raw), rc, wc_s, wu_s, ru, sc[6], g[6]);
-	gather_sample<7>(L, U, index_bits<IN16, 7>(raw), rc, wc_s, wu_s, ru, sc[7], g[7]);
+	gather_sample<0>(L, index_bits<IN16, 0>(raw), rc, sc[0], g[0]);
+	gather_sample<1>(L, index_bits<IN16, 1>(raw), rc, sc[1], g[1]);
+	gather_sample<2>(L, index_bits<IN16, 2>(raw), rc, sc[2], g[2]);
+	gather_sample<3>(L, index_bits<IN16, 3>(raw), rc, sc[3], g[3]);
+	gather_sample<4>(L, index_bits<IN16, 4>(raw), rc, sc[4], g[4]);
+	gather_sample<5>(L, index_bits<IN16, 5>(raw), rc, sc[5], g[5]);
+	gather_sample<6>(L, index_bits<IN16, 6>(raw), rc, sc[6], g[6]);
+	gather_sample<7>(L, index_bits<IN16, 7>(raw), rc, sc[7], g[7]);
 
-	// neighbours' edge samples (their own intensity selects their pattern slot), then the edge filter
-	// (vfgs_hw.c:250-259). Computed unconditionally with harmless addresses when there is no neighbour
-	// (lh/rh fall back to the lane's own window) and selected at the end: straight-line code, no branches.
+	// neighbours' edge samples (their own intensity selects their pattern slot); harmless addresses when there
+	// is no neighbour (lh/rh fall back to the lane's own window), selected at the end
+	const smem_addr_t offl = (smem_addr_t)(lds32(L.lut | (smem_addr_t)(((vl >> in_shift) & 0xffu) << 7)) >> 8);
+	int hl = lds_s8(L.lh + rc + offl), hr = 0;
+	smem_addr_t offr = 0;
+	if (!MERGE) {
+		offr = (smem_addr_t)(lds32(L.lut | (smem_addr_t)(((vr >> in_shift) & 0xffu) << 7)) >> 8);
+		hr = lds_s8(L.rh + rc + offr);
+	}
+
+	int own_sign = L.s_own, mul = L.pow16 * L.s_own; // sign of g[], factor of the scale multiply
+	if (w_cur) { // vertical overlap with the block-row above: warp-uniform branch, 2 (1) of 16 (8) lines
+		const int wc_s = w_cur * L.s_own, wu_s = w_up * U.s_own;
+		g[0] = gather_blend<0>(L, U, index_bits<IN16, 0>(raw), ru, wc_s, wu_s, g[0]);
+		g[1] = gather_blend<1>(L, U, index_bits<IN16, 1>(raw), ru, wc_s, wu_s, g[1]);
+		g[2] = gather_blend<2>(L, U, index_bits<IN16, 2>(raw), ru, wc_s, wu_s, g[2]);
+		g[3] = gather_blend<3>(L, U, index_bits<IN16, 3>(raw), ru, wc_s, wu_s, g[3]);
+		g[4] = gather_blend<4>(L, U, index_bits<IN16, 4>(raw), ru, wc_s, wu_s, g[4]);
+		g[5] = gather_blend<5>(L, U, index_bits<IN16, 5>(raw), ru, wc_s, wu_s, g[5]);
+		g[6] = gather_blend<6>(L, U, index_bits<IN16, 6>(raw), ru, wc_s, wu_s, g[6]);
+		g[7] = gather_blend<7>(L, U, index_bits<IN16, 7>(raw), ru, wc_s, wu_s, g[7]);
+		hl = (hl * (w_cur * L.s_l) + lds_s8(U.lh + ru + offl) * (w_up * U.s_l) + 16) >> 5;
+		if (!MERGE) hr = (hr * (w_cur * L.s_r) + lds_s8(U.rh + ru + offr) * (w_up * U.s_r) + 16) >> 5;
+		own_sign = 1; mul = L.pow16;
+	} else {
+		hl *= L.s_l;
+		if (!MERGE) hr *= L.s_r;
+	}
+
+	// block-edge filter (vfgs_hw.c:250-259): taps read unfiltered grain; the result goes back into g[]'s sign convention
 	if (MERGE) {
-		const smem_addr_t offn = (smem_addr_t)(lds32(L.lut | (smem_addr_t)(((vl >> in_shift) & 0xffu) << 7)) >> 8);
-		int h = lds_s8(L.lh + rc + offn);
-		if (w_cur) h = (h * (w_cur * L.s_l) + lds_s8(U.lh + ru + offn) * (w_up * U.s_l) + 16) >> 5;
-		else h *= L.s_l;
 		const int a = L.has_right ? g[7] : g[0], b = L.has_right ? g[6] : g[1];
-		const int f = (h + 3 * a + b + 2) >> 2; // taps read unfiltered neighbours
+		const int f = ((hl + 2 + own_sign * (3 * a + b)) >> 2) * own_sign;
 		g[0] = L.has_left ? f : g[0];
 		g[7] = L.has_right ? f : g[7];
 	} else {
-		const smem_addr_t offl = (smem_addr_t)(lds32(L.lut | (smem_addr_t)(((vl >> in_shift) & 0xffu) << 7)) >> 8);
-		const smem_addr_t offr = (smem_addr_t)(lds32(L.lut | (smem_addr_t)(((vr >> in_shift) & 0xffu) << 7)) >> 8);
-		int hl = lds_s8(L.lh + rc + offl), hr = lds_s8(L.rh + rc + offr);
-		if (w_cur) {
-			hl = (hl * (w_cur * L.s_l) + lds_s8(U.lh + ru + offl) * (w_up * U.s_l) + 16) >> 5;
-			hr = (hr * (w_cur * L.s_r) + lds_s8(U.rh + ru + offr) * (w_up * U.s_r) + 16) >> 5;
-		} else {
-			hl *= L.s_l; hr *= L.s_r;
-		}
-		const int f0 = (hl + 3 * g[0] + g[1] + 2) >> 2; // both taps read unfiltered neighbours
-		const int f7 = (g[6] + 3 * g[7] + hr + 2) >> 2;
+		const int f0 = ((hl + 2 + own_sign * (3 * g[0] + g[1])) >> 2) * own_sign;
+		const int f7 = ((hr + 2 + own_sign * (g[6] + 3 * g[7])) >> 2) * own_sign;
 		g[0] = L.has_left ? f0 : g[0];
 		g[7] = L.has_right ? f7 : g[7];
 	}
@@ -206,8 +225,8 @@ VFGS_HD void gather_line(const GatherLane& L, const GatherUp& U, int rc, int w_c
 		uint32_t r[4];
 #pragma unroll
 		for (int k = 0; k < 4; k++) {
-			const int a_lo = sc[2 * k] * (g[2 * k] * L.pow16) + kRound;
-			const int a_hi = sc[2 * k + 1] * (g[2 * k + 1] * L.pow16) + kRound;
+			const int a_lo = sc[2 * k] * (g[2 * k] * mul) + kRound;
+			const int a_hi = sc[2 * k + 1] * (g[2 * k + 1] * mul) + kRound;
 			const uint32_t d2 = prmt((uint32_t)a_lo, (uint32_t)a_hi, 0x7632);
 			const uint32_t v2 = min_u16x2(raw[k], 0x3fff3fffu);
 			r[k] = min_s16x2(add_max_s16x2(v2, d2, L.lo2), L.hi2);
@@ -226,7 +245,7 @@ VFGS_HD void gather_line(const GatherLane& L, const GatherUp& U, int rc, int w_c
 #pragma unroll
 		for (int e = 0; e < 8; e++) {
 			const int v = (int)((raw[e >> 2] >> ((e & 3) * 8)) & 0xff);
-			int x = v + ((sc[e] * (g[e] * L.pow16) + 0x8000) >> 16);
+			int x = v + ((sc[e] * (g[e] * mul) + 0x8000) >> 16);
 			x = x > hi ? hi : x;
 			o[e] = x < lo ? lo : x;
 		}

@@ -139,10 +139,15 @@ fgs_apply_kernel(const __grid_constant__ FgsParams p)
 #define VFGS_FAST_THREADS8 1024  // 16-bit in, 8-bit out
 #endif
 #ifndef VFGS_FAST_THREADS16
-#define VFGS_FAST_THREADS16 768  // 16-bit out (and 8-bit in, 8-bit out)
+#define VFGS_FAST_THREADS16 768  // 16-bit in, 16-bit out
 #endif
-template <bool IN16, bool OUT8> struct FastCta { static constexpr int threads = (IN16 && OUT8) ? VFGS_FAST_THREADS8 : VFGS_FAST_THREADS16; };
-inline int fast_threads(bool in16, bool out8) { return (in16 && out8) ? VFGS_FAST_THREADS8 : VFGS_FAST_THREADS16; }
+#ifndef VFGS_FAST_THREADS_IN8
+#define VFGS_FAST_THREADS_IN8 1024  // 8-bit in, 8-bit out (2 bytes per sample: issue-bound like the 8-bit-output kernel)
+#endif
+template <bool IN16, bool OUT8> struct FastCta {
+	static constexpr int threads = !IN16 ? VFGS_FAST_THREADS_IN8 : OUT8 ? VFGS_FAST_THREADS8 : VFGS_FAST_THREADS16;
+};
+inline int fast_threads(bool in16, bool out8) { return !in16 ? VFGS_FAST_THREADS_IN8 : out8 ? VFGS_FAST_THREADS8 : VFGS_FAST_THREADS16; }
 
 template <bool IN16, bool OUT8>
 __global__ void __launch_bounds__(FastCta<IN16, OUT8>::threads, 1)

@@ -18,6 +18,17 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 
+def steady(line, frames):
+    """frames/s of the pipeline itself from the CLI's own stats line: the time since library load minus the
+    one-off CUDA context creation and page-locked allocation (what a long run amortises)."""
+    import re
+    m = re.search(r"CUDA context ([0-9.]+) s, page-locked ring ([0-9.]+) s; ([0-9.]+) s since library load", line)
+    if not m:
+        return None
+    ctx, ring, total = (float(x) for x in m.groups())
+    return {"fps": frames / max(total - ctx - ring, 1e-9), "startup_seconds": ctx + ring, "cuda_context_seconds": ctx}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--width", type=int, default=3840)
@@ -39,11 +50,14 @@ def main():
 
     def run(exe, n, dst):
         t0 = time.perf_counter()
-        r = subprocess.run([exe] + base + ["-n", str(n), src, dst], capture_output=True, text=True)
+        r = subprocess.run([exe] + base + ["-n", str(n), src, dst], capture_output=True, text=True,
+                           env=dict(os.environ, VFGS_B200_PIPE_STATS="1"))
         dt = time.perf_counter() - t0
         assert r.returncode == 0, r.stderr
+        stats.append(r.stderr.strip().splitlines()[-1] if r.stderr.strip() else "")
         return dt
 
+    stats = []
     out_ref, out_new = os.path.join(tmp, "ref.yuv"), os.path.join(tmp, "new.yuv")
     t_ref = run(ref, a.ref_frames, out_ref)
     run(cli, 2, out_new)                       # warm-up: CUDA context creation, page-locking
@@ -56,7 +70,8 @@ def main():
         "reference_cli": {"frames": a.ref_frames, "seconds": t_ref, "fps": a.ref_frames / t_ref, "threads": 1},
         "cuda_cli": {"frames": a.frames, "seconds": t_new, "fps": a.frames / t_new,
                      "seconds_at_reference_frame_count": t_new_small},
-        "outputs_identical": same,
+        "outputs_identical": same, "pipeline_stats": stats[2] if len(stats) > 2 else "",
+        "cuda_cli_steady_state": steady(stats[2] if len(stats) > 2 else "", a.frames),
     }))
     for f in os.listdir(tmp):
         os.remove(os.path.join(tmp, f))

@@ -8,6 +8,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
+#include <thread>
 #include <vector>
 
 #include "../../include/vfgs_b200.h"

@@ -340,7 +340,9 @@ int run_frames_device(const vfgs_b200_planes& in, const vfgs_b200_planes& out, i
 	g_ctx.last_launch[4] = 0;
 	LaunchPlan lp;
 	plan_launches(p, g_bi, g_kernel_mode, in.y == out.y, g_ctx.max_smem_optin - 1024, g_ctx.fast_pad, lp);
-	if (int rc = launch_streams(epoch, d_streams, d_woffs, make_woff_params(p, lp.kind), n, g, frame0, stream)) return rc;
+	// the register table feeds the general kernel, the window-offset table the fast and gather kernels
+	if (int rc = launch_streams(epoch, lp.any_general ? d_streams : nullptr, (lp.any_fast || lp.any_gather) ? d_woffs : nullptr,
+	                            make_woff_params(p, lp.kind), n, g, frame0, stream)) return rc;
 	if (lp.any_fast)
 		if (int rc = launch_apply(lp.fast, stream, kFast)) return rc;
 	if (lp.any_gather)

@@ -54,7 +54,7 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gm
 
 // ---- LFSR registers per block -------------------------------------------------------------
 // states[(f * R + r) * spitch + 1 + b] = LFSR register of block b of block-row r of frame frame0 + f
-// (words 0 and nb + 1 of a row are padding); woffs, when not null, gets the same blocks' pattern-window
+// (words 0 and nb + 1 of a row are padding; states may be null when only the general kernel's table is not needed); woffs, when not null, gets the same blocks' pattern-window
 // offsets for the fast path (four uint16 per block: Y, U, V, unused). One warp per (frame, block-row): jump the epoch register
 // ahead by t = ((frame0 + f) (R - 1) + r) nb steps with the matrix powers pow2 (JumpTable as
 // uint32[64][32]; lane i owns output bit i, a ballot assembles the word), then walk the row 32 steps
@@ -83,13 +83,13 @@ lfsr_states_kernel(uint32_t epoch_state, const uint32_t* __restrict__ pow2, uint
 			if ((t >> (k0 + j)) & 1ull) s = __ballot_sync(0xffffffffu, __popc(rows[j] & s) & 1);
 	}
 	const uint32_t step32 = pow2[5 * 32 + lane];
-	uint32_t* dst = states + (size_t)warp * spitch;
-	if (lane == 0) { dst[0] = 0; dst[nb + 1] = 0; }
+	uint32_t* dst = states + (size_t)warp * spitch; // states == nullptr: only the window offsets are wanted
+	if (states && lane == 0) { dst[0] = 0; dst[nb + 1] = 0; }
 	for (int b0 = 0; b0 < nb; b0 += 32) {
 		const uint32_t next = __ballot_sync(0xffffffffu, __popc(step32 & s) & 1);
 		if (b0 + lane < nb) {
 			const uint32_t st = __funnelshift_r(s, next, lane);
-			dst[1 + b0 + lane] = st;
+			if (states) dst[1 + b0 + lane] = st;
 			if (woffs) { // pattern-window offsets of the block for the fast path, one 8-byte store
 				uint32_t o[3];
 				for (int c = 0; c < 3; c++) o[c] = window_offset(c, st, wp.off[c], wp.stride[c], wp.copy[c], wp.subx, wp.suby); // fast or gather format

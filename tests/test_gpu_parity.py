@@ -6,8 +6,8 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from tests.util import (Oracle, first_mismatch, load_golden, parse_output_key, program_case, sha,
-                        synth_frames)
+from tests.util import (RANDOM_STATES, Oracle, first_mismatch, load_golden, parse_output_key, program_case,
+                        program_random_state, sha, synth_frames)
 
 pytestmark = pytest.mark.gpu
 
@@ -304,6 +304,27 @@ def test_extreme_geometries(hw, w, h, n):
                 hw.force_general_kernel(0)
             assert np.array_equal(got, exp), (case, w, h, mode, first_mismatch(got, exp, w, h, meta["fmt"], n))
             assert hw.get_lfsr() == o.get_lfsr()
+
+
+@pytest.mark.parametrize("spec", RANDOM_STATES)
+def test_random_states(hw, spec):
+    """Random hardware states through the setters (formats, depths, pattern counts, shifts and ranges the cfg/
+    files do not reach: 8-bit 4:2:2 / 4:4:4, multi-pattern 4:4:4 chroma, -128 pattern bytes): every kernel == oracle."""
+    seed, depth, fmt = spec[0], spec[1], spec[2]
+    for (w, h, n) in ((520, 50, 2), (1024, 96, 1)):
+        for od in ((0, 8) if depth == 10 else (0,)):
+            frames = synth_frames(n, w, h, fmt, depth, seed=seed + od)
+            o = Oracle(); program_random_state(o, *spec)
+            exp = o.add_grain_frames(frames, n, w, h, od)
+            for mode in (0, 1, 2):
+                hw.reset(); program_random_state(hw, *spec)
+                hw.force_general_kernel(mode)
+                try:
+                    got = run_device(hw, frames, n, w, h, od, depth)
+                finally:
+                    hw.force_general_kernel(0)
+                assert np.array_equal(got, exp), (spec, w, h, od, mode, first_mismatch(got, exp, w, h, fmt, n))
+                assert hw.get_lfsr() == o.get_lfsr()
 
 
 def test_empty_batch_is_a_no_op(hw):

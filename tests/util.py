@@ -62,3 +62,38 @@ def build_emu() -> str:
         # those libvfgs_b200.so exports when a test has loaded it first
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wl,-Bsymbolic", "-Wno-unknown-pragmas", "-o", so, src], check=True)
     return so
+
+
+def program_random_state(target, seed: int, depth: int, fmt: str, nluma: int = 1, nchroma: int = 1, legal: int = 0,
+                         shift: int = 5, with_minus128: bool = False) -> None:
+    """Programs `target` (Oracle, Reference or VfgsHw: same setter names as src/vfgs_hw.h) with a random but
+    legal hardware state through the setters, in the order the reference's firmware uses (vfgs_main.c:750-760,
+    vfgs_fw.c:578-643): nluma / nchroma pattern slots selected by random pattern LUTs, random scale LUTs."""
+    rng = np.random.default_rng(seed)
+    sx, sy = {"420": (2, 2), "422": (2, 1), "444": (1, 1)}[fmt]
+    target.vfgs_set_depth(depth)
+    target.vfgs_set_chroma_subsampling(sx, sy)
+    lo = -128 if with_minus128 else -127
+    for i in range(nluma):
+        target.vfgs_set_luma_pattern(i, rng.integers(lo, 128, size=(64, 64), dtype=np.int8))
+    for i in range(nchroma):
+        # a full 64 x 64 buffer: the reference reads 64/csubx bytes every 64/csuby bytes (vfgs_hw.c:320-325), which
+        # for 4:2:2 reaches past a packed 64 x 32 array
+        target.vfgs_set_chroma_pattern(i, rng.integers(lo, 128, size=(64, 64), dtype=np.int8))
+    for c in range(3):
+        n = nluma if c == 0 else nchroma
+        slots = rng.integers(0, n, size=8)
+        plut = (np.repeat(slots, 32).astype(np.uint8) << 4) | rng.integers(0, 16, size=256, dtype=np.uint8)  # low nibble is ignored (>> 4)
+        target.vfgs_set_scale_lut(c, rng.integers(0, 256, size=256, dtype=np.uint8))
+        target.vfgs_set_pattern_lut(c, np.ascontiguousarray(plut.astype(np.uint8)))
+    target.vfgs_set_scale_shift(shift)
+    target.vfgs_set_legal_range(legal)
+    target.vfgs_set_seed(int(rng.integers(1, 1 << 31)))
+
+
+# (seed, depth, fmt, luma slots, chroma slots, legal range, scale shift, -128 bytes in the patterns)
+RANDOM_STATES = [
+    (1, 8, "422", 1, 1, 0, 2, False), (2, 8, "444", 1, 1, 1, 7, False), (3, 8, "444", 3, 2, 0, 4, False),
+    (4, 10, "422", 1, 4, 1, 3, False), (5, 10, "444", 8, 8, 0, 6, False), (6, 10, "420", 2, 1, 0, 2, False),
+    (7, 10, "420", 1, 1, 1, 7, True), (8, 8, "420", 5, 3, 0, 5, True), (9, 10, "444", 1, 1, 0, 5, False),
+]

@@ -361,7 +361,7 @@ def run_b200_arm(args):
     value = world * F * args.steps / (ms_max * 1e-3)
 
     # end to end through the host entry point: pinned host buffers, H2D + kernels + D2H timed
-    Fe = args.e2e_frames or int(max(8, min(128, 8e8 // in_bytes)))
+    Fe = min(F, args.e2e_frames or int(max(8, min(128, 2.4e9 // in_bytes))))
     h_in = torch.empty(Fe * samples, dtype=src.dtype).pin_memory()
     h_in.copy_(src[: Fe * samples])
     h_out = torch.empty(Fe * samples, dtype=dst.dtype).pin_memory()

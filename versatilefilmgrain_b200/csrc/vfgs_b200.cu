@@ -581,7 +581,7 @@ int vfgs_b200_add_grain_frames_host(const void* in, void* out, int nframes, int 
 	Context& c = g_ctx;
 	if (c.used_stream) { CUDA_TRY(cudaStreamSynchronize(c.last_stream)); c.used_stream = false; }
 
-	// chunk = as many frames as fit ~64 MB of input; the ring has kPipeSlots chunks in flight
+	// chunk = as many frames as fit ~64 MB of input (measured ahead of 16 and 32 MB chunks, scripts/e2e_sweep.sh); the ring has kPipeSlots chunks in flight
 	size_t chunk_bytes = 64u << 20;
 	int nslots = 3;
 	if (const char* e = getenv("VFGS_B200_CHUNK_MB")) { long v = atol(e); if (v > 0 && v <= 4096) chunk_bytes = (size_t)v << 20; }

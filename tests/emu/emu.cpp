@@ -114,7 +114,11 @@ extern "C" int emu_add_grain_frames(const void* state, const void* in, void* out
 	{ // window offsets of every block (the second table lfsr_states_kernel writes), in the serving kernel's format
 		const WoffParams wp = make_woff_params(p, lp.kind);
 		for (size_t i = 0; i < states.size(); i++)
-			for (int c = 0; c < 3; c++) woffs[i * 4 + c] = (uint16_t)window_offset(c, states[i], wp.off[c], wp.stride[c], wp.copy[c], wp.subx, wp.suby);
+		{
+			woffs[i * 4 + 0] = (uint16_t)window_offset<0>(states[i], wp.c[0]);
+			woffs[i * 4 + 1] = (uint16_t)window_offset<1>(states[i], wp.c[1]);
+			woffs[i * 4 + 2] = (uint16_t)window_offset<2>(states[i], wp.c[2]);
+		}
 	}
 	if (lp.any_fast) { // what fgs_apply_fast_kernel builds in shared memory
 		const FgsParams& f = lp.fast;

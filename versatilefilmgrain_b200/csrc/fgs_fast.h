@@ -332,18 +332,32 @@ VFGS_HD void fast_line(const FastLane& L, int rc, int w_cur, int w_up, const Fas
 // 16-sample blocks (copies shifted by 0 and 4 bytes) and of 2 for 8-sample blocks (0, 2, 4, 6).
 VFGS_HD int fast_copies(int block_samples) { return block_samples == 16 ? 2 : 4; }
 
-// Byte offset, inside the fast image, of a block's pattern window for component c: the +pattern or
-// -pattern copies according to the block's sign, among them the copy shifted by ox % 8 bytes (copy_bytes
-// apart), row oy, column ox rounded down to 8. copy_bytes == 0: plain oy * stride + ox (the gather kernel's
-// format). Precomputed per block by lfsr_states_kernel (FgsParams::woffs), so a lane only adds its column
-// and the line's row pitch.
-VFGS_HD uint32_t window_offset(int c, uint32_t state, const int off[2], int stride, int copy_bytes, int subx, int suby)
+// Per-component constants of the window-offset computation (host-made, make_woff_params).
+struct WoffComp {
+	int off0, doff;   // offset of the +pattern copies; -pattern copies minus +pattern copies (gather format: 0, 0x8000)
+	int ystride;      // bytes per row step: stepy * row pitch
+	int copy;         // bytes between column-shifted copies (0 in the gather format)
+	int kmask, kshift; // copy index = qx & kmask, aligned column = (qx >> kshift) * xmul
+	int xmul;
+};
+
+// Byte offset, inside the component's image, of a block's pattern window. The ten-bit fields of the register
+// (vfgs_hw.c:99-138; decode_offsets) are moved to the top of a word, so that field * 13 >> 10 (column bin qx, 0..12)
+// and field * 12 >> 10 (row bin qy, 0..11) are one multiply-high each; U's row field wraps around the word.
+//   fast format    +pattern or -pattern copies according to the block's sign, among them the copy in which the
+//                  window column (qx * 4 or qx * 2) sits on an 8-byte boundary, row qy * step, column rounded down to 8
+//   gather format  qy * step * pitch + qx * step, bit 15 set when the block's sign is negative
+// Precomputed per block by lfsr_states_kernel (FgsParams::woffs), so a lane only adds its column and the line's row pitch.
+template <int C>
+VFGS_HD uint32_t window_offset(uint32_t s, const WoffComp& w)
 {
-	const BlockOfs o = decode_offsets(c, state, subx, suby);
-	const int base = off[o.sign < 0 ? 1 : 0] + o.oy * stride;
-	if (!copy_bytes) return (uint32_t)(base + o.ox);
-	const int k = (c && subx > 1) ? (o.ox >> 1) & 3 : (o.ox >> 2) & 1;
-	return (uint32_t)(base + k * copy_bytes + (o.ox & ~7));
+	constexpr uint32_t kTop = 0xffc00000u; // the bits below a field must not carry into the product
+	const uint32_t xtop = C == 0 ? s << 22 : C == 1 ? (s << 12) & kTop : (s << 2) & kTop;
+	const uint32_t ytop = C == 0 ? (s << 8) & kTop : C == 1 ? ((s << 30) | ((s >> 2) & 0x3fc00000u)) : (s << 18) & kTop;
+	const uint32_t sign = C == 0 ? s >> 31 : C == 1 ? (s >> 2) & 1u : (s >> 15) & 1u;
+	const uint32_t qx = mulhi_u32(xtop, 13u), qy = mulhi_u32(ytop, 12u);
+	return (uint32_t)w.off0 + sign * (uint32_t)w.doff + qy * (uint32_t)w.ystride + (qx & (uint32_t)w.kmask) * (uint32_t)w.copy +
+	       (qx >> w.kshift) * (uint32_t)w.xmul;
 }
 
 #ifndef VFGS_FAST_LB

@@ -91,10 +91,9 @@ lfsr_states_kernel(uint32_t epoch_state, const uint32_t* __restrict__ pow2, uint
 			const uint32_t st = __funnelshift_r(s, next, lane);
 			if (states) dst[1 + b0 + lane] = st;
 			if (woffs) { // pattern-window offsets of the block for the fast path, one 8-byte store
-				uint32_t o[3];
-				for (int c = 0; c < 3; c++) o[c] = window_offset(c, st, wp.off[c], wp.stride[c], wp.copy[c], wp.subx, wp.suby); // fast or gather format
-				uint2 v;
-				v.x = o[0] | (o[1] << 16); v.y = o[2];
+				uint2 v; // fast or gather format, per component
+				v.x = window_offset<0>(st, wp.c[0]) | (window_offset<1>(st, wp.c[1]) << 16);
+				v.y = window_offset<2>(st, wp.c[2]);
 				*(uint2*)(woffs + ((size_t)warp * spitch + 1 + b0 + lane) * 4) = v;
 			}
 		}

@@ -278,18 +278,22 @@ inline void plan_launches(const FgsParams& p, const TableInfo& bi, int mode, boo
 //           copy shifted by ox % 8, + oy * stride + ox rounded down to 8
 //   gather  oy * stride + ox inside a pattern slot, bit 15 set when the block sign is negative
 struct WoffParams {
-	int gather[3];
-	int off[3][2], stride[3], copy[3], subx, suby; // copy: 0 for the gather format
+	WoffComp c[3];
 };
 inline WoffParams make_woff_params(const FgsParams& p, const int kind[3])
 {
 	WoffParams w;
 	for (int c = 0; c < 3; c++) {
-		w.gather[c] = kind[c] == 1;
-		if (w.gather[c]) { w.off[c][0] = 0; w.off[c][1] = 0x8000; w.stride[c] = p.pat_stride[c ? 1 : 0]; w.copy[c] = 0; }
-		else { w.off[c][0] = p.fpat_off[c][0]; w.off[c][1] = p.fpat_off[c][1]; w.stride[c] = p.fpat_stride[c]; w.copy[c] = p.fpat_copy[c]; }
+		const int stepx = (c && p.subx > 1) ? 2 : 4, stepy = (c && p.suby > 1) ? 2 : 4; // vfgs_hw.c:103-137
+		WoffComp& k = w.c[c];
+		if (kind[c] == 1) { // gather format
+			k.off0 = 0; k.doff = 0x8000; k.ystride = stepy * p.pat_stride[c ? 1 : 0];
+			k.copy = 0; k.kmask = 0; k.kshift = 0; k.xmul = stepx;
+		} else {            // fast format: 2 copies (columns multiples of 4) or 4 (multiples of 2)
+			k.off0 = p.fpat_off[c][0]; k.doff = p.fpat_off[c][1] - p.fpat_off[c][0]; k.ystride = stepy * p.fpat_stride[c];
+			k.copy = p.fpat_copy[c]; k.kmask = stepx == 4 ? 1 : 3; k.kshift = stepx == 4 ? 1 : 2; k.xmul = 8;
+		}
 	}
-	w.subx = p.subx; w.suby = p.suby;
 	return w;
 }
 

@@ -44,6 +44,7 @@ WORKLOADS = {
     "4k420_afgs1_10to10": ("fgs_afgs1_test1.cfg|d10|420|g100", 3840, 2160, "420", 10, 0),
     "4k420_afgs1_10to8": ("fgs_afgs1_test1.cfg|d10|420|g100", 3840, 2160, "420", 10, 8),
     "4k420_afgs1_8to8": ("fgs_afgs1_test1.cfg|d8|420|g100", 3840, 2160, "420", 8, 0),
+    "1366x768_ragged": ("fgs_afgs1_test1.cfg|d10|420|g100", 1366, 768, "420", 10, 0),  # rows not 16-byte aligned: general kernel
     "4k420_sei_default": ("fgs_sei.cfg|d10|420|g100", 3840, 2160, "420", 10, 0),
     "4k420_ff_test5": ("fgs_sei_ff_test5.cfg|d10|420|g100", 3840, 2160, "420", 10, 0),
     "1080p420_ff_test1": ("fgs_sei_ff_test1.cfg|d10|420|g100", 1920, 1080, "420", 10, 0),

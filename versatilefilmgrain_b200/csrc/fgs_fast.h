@@ -6,15 +6,19 @@
 // samples, neighbours' edge samples recomputed from their own LFSR window), but the per-sample work
 // is cut to the bone:
 //   * with one pattern slot the unscaled grain does not depend on the sample, so a lane's 8 grain
-//     bytes per line are one contiguous octet of a pattern row: two/three 32-bit shared loads;
+//     bytes per line are one contiguous octet of a pattern row: one 64-bit shared load (the image
+//     keeps column-shifted copies so that every window starts on an 8-byte boundary, and skews the
+//     row pitch so that the windows of a line spread over all banks);
 //   * the block's random sign (vfgs_hw.c:218 "* s") is folded into WHICH COPY of the pattern is
 //     read: the table image holds +pattern and -pattern (the host only takes this path when no
 //     pattern byte is -128), so no per-sample sign multiply is left;
-//   * the scale LUT (vfgs_hw.c:239) is replicated per lane in shared memory ([256][32] words,
-//     word = sLUT[Y] | sLUT[U] << 8 | sLUT[V] << 16): a lane only ever touches its own bank, so the
-//     256-entry lookup with random intensities is conflict-free by construction;
+//   * the scale LUT (vfgs_hw.c:239) is replicated per lane in shared memory, one table of
+//     [256][32] words = scale << (16 - shift) per component: a lane only ever touches its own bank,
+//     so the 256-entry lookup with random intensities is conflict-free by construction, and the
+//     rounded shift of vfgs_hw.c:263 is the upper half-word of one multiply-add;
 //   * add + clip (vfgs_hw.c:265-267) run on two samples at a time with the packed 16-bit min/max
-//     instructions (VIADDMNMX / VIMNMX .S16x2); 10-bit samples stay packed in their load words.
+//     instructions (VIADDMNMX / VIMNMX .S16x2); 10-bit samples stay packed in their load words,
+//     8-bit samples are widened two at a time into the same form.
 // Host-compilable like fgs_task.h (tests/emu) -- the helpers below emulate the few PTX instructions.
 #pragma once
 #include <stddef.h>
@@ -207,9 +211,9 @@ VFGS_HD void octet(smem_addr_t a, uint32_t& w0, uint32_t& w1)
 // exactly one block edge (its left end if it is the first half, else its right end), so one halo address
 // and one filter can serve (MergeHalo): lh. With 8-sample blocks the lane is a whole block and has both.
 // Measured on B200 (scripts/ab_sweep.sh, same box): the merged form is +3 points of HBM roofline for the
-// issue-bound 8-bit-output kernel and -4 points for the HBM-bound 16-bit-output kernel, hence mode 2.
+// issue-bound 8-bit-output kernel and neutral for the HBM-bound 16-bit-output kernel at its CTA size.
 #ifndef VFGS_FAST_MERGE_HALO
-#define VFGS_FAST_MERGE_HALO 2 // 0 never, 1 always, 2 only with 8-bit output or input
+#define VFGS_FAST_MERGE_HALO 1 // 0 never, 1 always, 2 only with 8-bit output or input (build-time knob for experiments)
 #endif
 template <bool IN16, bool OUT8> struct MergeHalo { // mode 2: the issue-bound variants (8-bit output, 8-bit input)
 	static constexpr bool value = VFGS_FAST_MERGE_HALO == 1 || (VFGS_FAST_MERGE_HALO == 2 && (OUT8 || !IN16));

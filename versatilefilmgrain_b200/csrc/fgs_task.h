@@ -277,12 +277,16 @@ VFGS_HD void process_task(const FgsParams& p, const uint8_t* tab, uint32_t task,
 				} else {
 					// picture tail or unaligned rows: sample by sample, zero right of the picture
 					int s[8];
+#pragma unroll
 					for (int e = 0; e < 8; e++) s[e] = (k0 + e < pl.width) ? ld_sample(row, k0 + e, p.in_bytes) : 0;
-					if (p.in_bytes == 2)
+					if (p.in_bytes == 2) {
+#pragma unroll
 						for (int e = 0; e < 4; e++) raw[q][e] = (uint32_t)s[2 * e] | ((uint32_t)s[2 * e + 1] << 16);
-					else
+					} else {
+#pragma unroll
 						for (int e = 0; e < 2; e++)
 							raw[q][e] = (uint32_t)s[4 * e] | ((uint32_t)s[4 * e + 1] << 8) | ((uint32_t)s[4 * e + 2] << 16) | ((uint32_t)s[4 * e + 3] << 24);
+					}
 				}
 				vl[q] = (need_nb && L.has_left) ? ld_sample(row, k0 - 1, p.in_bytes) : 0;
 				vr[q] = (need_nb && L.has_right && k0 + 8 < pl.width) ? ld_sample(row, k0 + 8, p.in_bytes) : 0;
@@ -321,6 +325,7 @@ VFGS_HD void process_task(const FgsParams& p, const uint8_t* tab, uint32_t task,
 						st_global_8(orow + k0, w);
 					}
 				} else {
+#pragma unroll
 					for (int e = 0; e < 8; e++)
 						if (k0 + e < pl.width) {
 							if (p.out_bytes == 2) ((uint16_t*)orow)[k0 + e] = (uint16_t)o[e];

@@ -102,7 +102,11 @@ lfsr_states_kernel(uint32_t epoch_state, const uint32_t* __restrict__ pow2, uint
 }
 
 // ---- grain synthesis -----------------------------------------------------------------------
-__global__ void __launch_bounds__(kCtaThreads, 4)
+// the general task code wants ~128 registers: 2 CTAs per SM without spills measured ahead of 4 with (1366 x 768: 912 vs 681 GB/s)
+#ifndef VFGS_GENERAL_CTAS
+#define VFGS_GENERAL_CTAS 2
+#endif
+__global__ void __launch_bounds__(kCtaThreads, VFGS_GENERAL_CTAS)
 fgs_apply_kernel(const __grid_constant__ FgsParams p)
 {
 	extern __shared__ __align__(128) uint8_t tab[];

@@ -48,10 +48,20 @@ VFGS_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
 	return d;
 #endif
 }
-// sign-extended byte e (0..7) of the octet {w1,w0}
-template <int E>
+// sign-extended byte e (0..7) of the octet {w1,w0}. FMA_TOP: the top byte of each word comes out of a multiply-high
+// (arithmetic shift by 24 on the FMA pipe): the ALU pipe is the busier one in the issue-bound variants (8-bit output
+// or input: +0.3 / +5 points measured); the HBM-bound 16-bit variant loses 2 points with it and keeps the PRMT.
+template <int E, bool FMA_TOP = false>
 VFGS_HD int octet_byte(uint32_t w0, uint32_t w1)
 {
+	if (FMA_TOP && (E == 3 || E == 7)) {
+		const int w = (int)(E == 3 ? w0 : w1);
+#if defined(__CUDA_ARCH__)
+		return __mulhi(w, 256);
+#else
+		return (int)(((long long)w * 256) >> 32);
+#endif
+	}
 	constexpr uint32_t n = (uint32_t)E, s = 8u | (uint32_t)E;
 	return (int)prmt(w0, w1, n | (s << 4) | (s << 8) | (s << 12));
 }
@@ -237,6 +247,26 @@ VFGS_HD int blend(int cur, uint32_t u0, uint32_t u1, int w_cur, int w_up) // vfg
 	return (cur * w_cur + octet_byte<E>(u0, u1) * w_up + 16) >> 5;
 }
 
+// Scale, add, clip (vfgs_hw.c:239, 260-267) of 8 samples held in two words of four bytes: widened two at a time
+// into the 16x2 form of the 16-bit path (no cap needed: v <= 255); LUT index = sample (vfgs_hw.c:211), times 128.
+VFGS_HD void scale_add_clip_8bit(smem_addr_t lut, uint32_t lo2, uint32_t hi2, const int g[8], uint32_t raw0, uint32_t raw1,
+                                 uint32_t& out0, uint32_t& out1)
+{
+	uint32_t r[4];
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		const uint32_t v2 = prmt(k < 2 ? raw0 : raw1, 0u, (k & 1) ? 0x4342 : 0x4140);
+		const int s_lo = (int)lds32(lut | (smem_addr_t)((v2 << 7) & 0x7f80u));
+		const int s_hi = (int)lds32(lut | (smem_addr_t)(mulhi_u32(v2, 1u << 23) & 0x7f80u)); // v2 >> 9 on the FMA pipe
+		const int a_lo = s_lo * g[2 * k] + 0x8000;
+		const int a_hi = s_hi * g[2 * k + 1] + 0x8000;
+		const uint32_t d2 = prmt((uint32_t)a_lo, (uint32_t)a_hi, 0x7632);
+		r[k] = min_s16x2(add_max_s16x2(v2, d2, lo2), hi2);
+	}
+	out0 = prmt(r[0], r[1], 0x6420);
+	out1 = prmt(r[2], r[3], 0x6420);
+}
+
 // One line of one lane. raw: the lane's 8 samples as loaded (IN16: 4 words of two 10-bit samples,
 // else 2 words of four bytes). outw: result words ready to store (16-bit out: 4 words, 8-bit: 2).
 // rc: byte offset of this line's row inside the current block's window; w_cur != 0 selects the
@@ -248,8 +278,9 @@ VFGS_HD void fast_line(const FastLane& L, int rc, int w_cur, int w_up, const Fas
 	uint32_t c0, c1;
 	octet(L.own + rc, c0, c1);
 	int g[8];
-	g[0] = octet_byte<0>(c0, c1); g[1] = octet_byte<1>(c0, c1); g[2] = octet_byte<2>(c0, c1); g[3] = octet_byte<3>(c0, c1);
-	g[4] = octet_byte<4>(c0, c1); g[5] = octet_byte<5>(c0, c1); g[6] = octet_byte<6>(c0, c1); g[7] = octet_byte<7>(c0, c1);
+	constexpr bool kFmaTop = OUT8 || !IN16;
+	g[0] = octet_byte<0>(c0, c1); g[1] = octet_byte<1>(c0, c1); g[2] = octet_byte<2>(c0, c1); g[3] = octet_byte<3, kFmaTop>(c0, c1);
+	g[4] = octet_byte<4>(c0, c1); g[5] = octet_byte<5>(c0, c1); g[6] = octet_byte<6>(c0, c1); g[7] = octet_byte<7, kFmaTop>(c0, c1);
 	if (MergeHalo<IN16, OUT8>::value && NSH == 4) {
 		// one edge per lane: halo h next to a, then b (left edge: h | g0 g1, right edge: g6 g7 | h mirrored)
 		const bool edge = L.has_left || L.has_right;
@@ -315,20 +346,7 @@ VFGS_HD void fast_line(const FastLane& L, int rc, int w_cur, int w_up, const Fas
 			outw[0] = r[0]; outw[1] = r[1]; outw[2] = r[2]; outw[3] = r[3];
 		}
 	} else {
-		// 8-bit samples: widened two at a time into the 16x2 form of the 16-bit path (no cap needed: v <= 255)
-		uint32_t r[4];
-#pragma unroll
-		for (int k = 0; k < 4; k++) {
-			const uint32_t v2 = prmt(raw[k >> 1], 0u, (k & 1) ? 0x4342 : 0x4140); // bytes 2k', 2k'+1 of the word, zero-extended
-			const int s_lo = (int)lds32(L.lut | (smem_addr_t)((v2 << 7) & 0x7f80u));  // LUT index = sample (vfgs_hw.c:211), times 128
-			const int s_hi = (int)lds32(L.lut | (smem_addr_t)((v2 >> 9) & 0x7f80u));
-			const int a_lo = s_lo * g[2 * k] + 0x8000;
-			const int a_hi = s_hi * g[2 * k + 1] + 0x8000;
-			const uint32_t d2 = prmt((uint32_t)a_lo, (uint32_t)a_hi, 0x7632);
-			r[k] = min_s16x2(add_max_s16x2(v2, d2, L.lo2), L.hi2);  // vfgs_hw.c:267
-		}
-		outw[0] = prmt(r[0], r[1], 0x6420);
-		outw[1] = prmt(r[2], r[3], 0x6420);
+		scale_add_clip_8bit(L.lut, L.lo2, L.hi2, g, raw[0], raw[1], outw[0], outw[1]);
 	}
 }
 
@@ -471,11 +489,145 @@ VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, const TaskGeom&
 	else lines(std::false_type());
 }
 
+// ---- 8-bit input, 16 samples per lane ------------------------------------------------------
+// With 8-bit samples a 128-bit access holds 16 samples, so a lane can own a whole 16-sample block (or two
+// 8-sample blocks): the per-line work that does not depend on the sample count (addresses, loop control,
+// halo loads, edge filters without left/right selection) and the per-task set-up are spread over twice the
+// samples. Taken when the component's width is a multiple of 16 and its rows are 16-byte aligned.
+struct WideLane {
+	smem_addr_t own0, own1;  // pattern rows of line j = 0: samples 0..7 and 8..15 (two blocks when the block size is 8)
+	smem_addr_t lh, rh;      // halo bytes: last column of the block to the left / first column of the block to the right
+	smem_addr_t lut;
+	int stride;
+	bool has_left, has_right;
+	uint32_t lo2, hi2;
+};
+struct WideUp {
+	smem_addr_t own0, own1, lh, rh;
+};
+
+VFGS_HD void octet_to_ints(uint32_t w0, uint32_t w1, int g[8])
+{
+	g[0] = octet_byte<0>(w0, w1); g[1] = octet_byte<1>(w0, w1); g[2] = octet_byte<2>(w0, w1); g[3] = octet_byte<3, true>(w0, w1);
+	g[4] = octet_byte<4>(w0, w1); g[5] = octet_byte<5>(w0, w1); g[6] = octet_byte<6>(w0, w1); g[7] = octet_byte<7, true>(w0, w1);
+}
+VFGS_HD void blend_octet(int g[8], uint32_t u0, uint32_t u1, int w_cur, int w_up)
+{
+	g[0] = blend<0>(g[0], u0, u1, w_cur, w_up); g[1] = blend<1>(g[1], u0, u1, w_cur, w_up);
+	g[2] = blend<2>(g[2], u0, u1, w_cur, w_up); g[3] = blend<3>(g[3], u0, u1, w_cur, w_up);
+	g[4] = blend<4>(g[4], u0, u1, w_cur, w_up); g[5] = blend<5>(g[5], u0, u1, w_cur, w_up);
+	g[6] = blend<6>(g[6], u0, u1, w_cur, w_up); g[7] = blend<7>(g[7], u0, u1, w_cur, w_up);
+}
+// One line of one wide lane: 16 samples in raw[4] (four bytes per word), result in outw[4].
+template <int NSH>
+VFGS_HD void wide_line(const WideLane& L, int rc, int w_cur, int w_up, const WideUp& U, int ru,
+                       const uint32_t raw[4], uint32_t outw[4])
+{
+	uint32_t a0, a1, b0, b1;
+	octet(L.own0 + rc, a0, a1);
+	octet(L.own1 + rc, b0, b1);
+	int ga[8], gb[8];
+	octet_to_ints(a0, a1, ga);
+	octet_to_ints(b0, b1, gb);
+	int hl = L.has_left ? lds_s8(L.lh + rc) : 0;
+	int hr = L.has_right ? lds_s8(L.rh + rc) : 0;
+	if (w_cur) { // vertical overlap with the block-row above (vfgs_hw.c:173-188, 223-229)
+		uint32_t u0, u1;
+		octet(U.own0 + ru, u0, u1);
+		blend_octet(ga, u0, u1, w_cur, w_up);
+		octet(U.own1 + ru, u0, u1);
+		blend_octet(gb, u0, u1, w_cur, w_up);
+		if (L.has_left) hl = (hl * w_cur + lds_s8(U.lh + ru) * w_up + 16) >> 5;
+		if (L.has_right) hr = (hr * w_cur + lds_s8(U.rh + ru) * w_up + 16) >> 5;
+	}
+	// block-edge filters (vfgs_hw.c:250-259), taps read unfiltered grain
+	const int f0 = (hl + 3 * ga[0] + ga[1] + 2) >> 2;
+	const int f15 = (gb[6] + 3 * gb[7] + hr + 2) >> 2;
+	if (NSH == 3) { // the lane holds two 8-sample blocks: the edge between them is lane-internal
+		const int f7 = (ga[6] + 3 * ga[7] + gb[0] + 2) >> 2;
+		const int f8 = (ga[7] + 3 * gb[0] + gb[1] + 2) >> 2;
+		ga[7] = f7; gb[0] = f8;
+	}
+	ga[0] = L.has_left ? f0 : ga[0];
+	gb[7] = L.has_right ? f15 : gb[7];
+	scale_add_clip_8bit(L.lut, L.lo2, L.hi2, ga, raw[0], raw[1], outw[0], outw[1]);
+	scale_add_clip_8bit(L.lut, L.lo2, L.hi2, gb, raw[2], raw[3], outw[2], outw[3]);
+}
+
+template <int NSH>
+VFGS_HD void wide_task_body(const FgsParams& p, smem_addr_t lut, const TaskGeom& t, int k0, int lane)
+{
+	const int c = t.c;
+	const smem_addr_t img = lut + (smem_addr_t)(ptrdiff_t)p.fimg_off[c];
+	const Plane& pl = p.comp[c];
+	const int ysh = (c && p.suby > 1) ? 1 : 0;
+	constexpr int n = 1 << NSH;
+	constexpr int LB = VFGS_FAST_LB16;
+
+	const int cl0 = (t.r * 16) >> ysh;
+	int cl1 = cl0 + (16 >> ysh);
+	if (cl1 > pl.lines) cl1 = pl.lines;
+	const int nl = cl1 - cl0;
+	if (nl <= 0) return;
+
+	const long long in_pitch = pl.in_row_bytes, out_pitch = pl.out_row_bytes;
+	const uint8_t* src = pl.in + (long long)t.f * p.in_frame_bytes + (long long)cl0 * in_pitch + (long long)k0;
+	uint8_t* dst = pl.out + (long long)t.f * p.out_frame_bytes + (long long)cl0 * out_pitch + (long long)k0;
+
+	uint32_t raw[LB][4];
+#pragma unroll
+	for (int q = 0; q < LB; q++) ld_global_16(src + (q < nl ? q : nl - 1) * in_pitch, raw[q]);
+
+	// first and last block of the lane (the same one with 16-sample blocks)
+	const int b0 = k0 >> NSH, b1 = (k0 + 15) >> NSH;
+	WideLane L;
+	L.has_left = b0 > 0;
+	L.has_right = b1 + 1 < p.nb;
+	L.stride = p.fpat_stride[c];
+	L.lut = lut + (smem_addr_t)(c * kLutBytes + lane * 4);
+	L.lo2 = (uint32_t)p.lo[c] * 0x00010001u; L.hi2 = (uint32_t)p.hi[c] * 0x00010001u;
+
+	const int srow = t.r - p.stream_row0;
+	const uint16_t* w_cur = p.woffs + (((long long)t.f * p.stream_rows + srow) * p.spitch + 1 + b0) * 4 + c;
+	auto windows = [&](const uint16_t* w, smem_addr_t& own0, smem_addr_t& own1, smem_addr_t& lh, smem_addr_t& rh) {
+		own0 = img + (smem_addr_t)w[0];
+		own1 = NSH == 4 ? own0 + 8 : img + (smem_addr_t)w[4];
+		lh = rh = own0;
+		if (L.has_left) lh = img + (smem_addr_t)(w[-4] + n - 1);
+		if (L.has_right) rh = img + (smem_addr_t)w[NSH == 4 ? 4 : 8];
+	};
+	windows(w_cur, L.own0, L.own1, L.lh, L.rh);
+	WideUp U;
+	U.own0 = U.own1 = U.lh = U.rh = L.own0;
+	bool ovl = t.r > 0;
+	if (ovl) windows(w_cur - p.spitch * 4, U.own0, U.own1, U.lh, U.rh);
+
+	int rc = 0;
+	const uint8_t* nxt = src + LB * in_pitch;
+#pragma unroll 1
+	for (int base = 0; base < nl; base += LB) {
+#pragma unroll
+		for (int q = 0; q < LB; q++) {
+			const int line = base + q;
+			uint32_t w[4];
+			int wc = 0, wu = 0, ru = 0;
+			if (q == 0 && ovl) { wc = ysh ? 20 : 12; wu = ysh ? 20 : 24; ru = (16 >> ysh) * L.stride; }
+			if (q == 1 && ovl && !ysh) { wc = 24; wu = 12; ru = 17 * L.stride; }
+			wide_line<NSH>(L, rc, wc, wu, U, ru, raw[q], w);
+			ld_global_16_if(nxt, raw[q], line + LB < nl);
+			if (line < nl) st_global_16(dst, w);
+			rc += L.stride; nxt += in_pitch; dst += out_pitch;
+		}
+		ovl = false;
+	}
+}
+
 // Dispatch on the component's block size (16 samples: luma and non-subsampled chroma; 8: chroma
 // subsampled horizontally).
 // Fast-kernel task numbering: per frame the components one after the other; inside a component the
-// stripes' rows are one flat run of lane units (8 samples), 32 consecutive units per warp-task, so only
-// the very last task of a component can have idle lanes (a row need not be a multiple of 256 samples).
+// stripes' rows are one flat run of lane units (8 samples, or 16 on the wide 8-bit path: FgsParams::fwide), 32
+// consecutive units per warp-task, so only the very last task of a component can have idle lanes (a row need
+// not be a multiple of 256 samples).
 template <bool IN16, bool OUT8>
 VFGS_HD void process_task_fast(const FgsParams& p, smem_addr_t lut, uint32_t task, int lane)
 {
@@ -491,6 +643,12 @@ VFGS_HD void process_task_fast(const FgsParams& p, smem_addr_t lut, uint32_t tas
 	const uint32_t row = fastdiv(unit, p.div_funits[t.c]);
 	t.r = p.row_begin + (int)row;
 	t.seg = 0;
+	if (!IN16 && p.fwide[t.c]) { // 8-bit samples, 16 per lane
+		const int k0 = (int)(unit - row * upr) * 16;
+		if (t.c && p.subx > 1) wide_task_body<3>(p, lut, t, k0, lane);
+		else wide_task_body<4>(p, lut, t, k0, lane);
+		return;
+	}
 	const int k0 = (int)(unit - row * upr) * kSamplesPerLane;
 	if (t.c && p.subx > 1) fast_task_body<IN16, OUT8, 3>(p, lut, t, k0, lane);
 	else fast_task_body<IN16, OUT8, 4>(p, lut, t, k0, lane);

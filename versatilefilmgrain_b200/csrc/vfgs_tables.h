@@ -11,6 +11,9 @@
 #ifndef VFGS_PAT_ROW_SKEW
 #define VFGS_PAT_ROW_SKEW 8 // bytes (general image: gather and general kernels; build-time knob for experiments)
 #endif
+#ifndef VFGS_FAST_WIDE8
+#define VFGS_FAST_WIDE8 1 // 8-bit input: 16 samples per lane where possible (build-time knob for experiments)
+#endif
 #ifndef VFGS_FAST_ROW_SKEW
 #define VFGS_FAST_ROW_SKEW 8 // bytes, multiple of 8 (build-time knob for experiments)
 #endif
@@ -255,7 +258,11 @@ inline void plan_launches(const FgsParams& p, const TableInfo& bi, int mode, boo
 		FgsParams& f = lp.fast;
 		f.ftasks_per_frame = 0;
 		for (int c = 0; c < 3; c++) {
-			f.funits_per_row[c] = kind[c] == 0 ? f.comp[c].width / kSamplesPerLane : 0;
+			// 8-bit samples: 16 per lane where the rows allow 128-bit accesses
+			f.fwide[c] = VFGS_FAST_WIDE8 && kind[c] == 0 && f.in_bytes == 1 && f.comp[c].width % 16 == 0 &&
+			             aligned_for(f.comp[c].in, f.comp[c].in_row_bytes, f.in_frame_bytes, 16) &&
+			             aligned_for(f.comp[c].out, f.comp[c].out_row_bytes, f.out_frame_bytes, 16);
+			f.funits_per_row[c] = kind[c] == 0 ? f.comp[c].width / (f.fwide[c] ? 16 : kSamplesPerLane) : 0;
 			f.ftasks[c] = (f.funits_per_row[c] * f.rows + 31) / 32;
 			f.ftasks_per_frame += f.ftasks[c];
 			f.div_funits[c] = make_fastdiv((uint32_t)(f.funits_per_row[c] > 0 ? f.funits_per_row[c] : 1));

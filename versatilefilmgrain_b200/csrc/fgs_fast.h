@@ -386,6 +386,7 @@ VFGS_HD uint32_t window_offset(uint32_t s, const WoffComp& w)
 #define VFGS_FAST_LB 4
 #endif
 constexpr int kFastLB = VFGS_FAST_LB; // lines in flight per lane (build-time knob for experiments)
+static_assert(kFastLB >= 2, "both vertical-overlap lines of a block-row must fall into the first group of lines");
 #ifndef VFGS_FAST_LB16
 #define VFGS_FAST_LB16 VFGS_FAST_LB // fast kernel, 16-bit (or 8-bit in, 8-bit out) stores
 #endif

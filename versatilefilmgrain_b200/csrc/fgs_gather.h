@@ -19,6 +19,13 @@ namespace vfgs {
 
 // Shared memory: [0, 32 KB * ngather) private LUTs of the gather components (each on a 32 KB
 // boundary), then the general table image's pattern slots (gpat_off, relative to the image copy).
+#ifndef VFGS_GATHER_LB
+#define VFGS_GATHER_LB 2 // 2 lines in flight with 28 warps per SM measured ahead of 3, 4 and 5 with 24 (the kernel is issue-bound;
+                         // fewer staging registers leave it free of spills)
+#endif
+constexpr int kGatherLB = VFGS_GATHER_LB; // lines in flight per lane
+static_assert(kGatherLB >= 2, "both vertical-overlap lines of a block-row must fall into the first group of lines");
+
 struct GatherLane {
 	smem_addr_t own;        // bank + window row 0 + ox + i0 of the current block (slot offset added per sample)
 	smem_addr_t lh, rh;     // neighbour windows: last column of block b-1 / first column of block b+1
@@ -299,9 +306,9 @@ VFGS_HD void gather_task_body(const FgsParams& p, smem_addr_t luts, smem_addr_t 
 
 	// vl/vr: neighbour samples fetched from memory (kept apart from raw: combining them would wait for the loads
 	// just issued); MERGE keeps the lane's one neighbour in vl
-	uint32_t raw[kFastLB][4] = {}, vl[kFastLB], vr[kFastLB];
+	uint32_t raw[kGatherLB][4] = {}, vl[kGatherLB], vr[kGatherLB];
 #pragma unroll
-	for (int q = 0; q < kFastLB; q++) {
+	for (int q = 0; q < kGatherLB; q++) {
 		const uint8_t* row = src + (q < nl ? q : nl - 1) * in_pitch;
 		if (active) {
 			if (IN16) ld_global_16(row, raw[q]);
@@ -342,11 +349,11 @@ VFGS_HD void gather_task_body(const FgsParams& p, smem_addr_t luts, smem_addr_t 
 	}
 
 	int rc = 0;
-	const uint8_t* nxt = src + kFastLB * in_pitch;
+	const uint8_t* nxt = src + kGatherLB * in_pitch;
 #pragma unroll 1
-	for (int base = 0; base < nl; base += kFastLB) {
+	for (int base = 0; base < nl; base += kGatherLB) {
 #pragma unroll
-		for (int q = 0; q < kFastLB; q++) {
+		for (int q = 0; q < kGatherLB; q++) {
 			const int line = base + q;
 			uint32_t w[4];
 			int w_cur = 0, w_up = 0, ru = 0;
@@ -356,7 +363,7 @@ VFGS_HD void gather_task_body(const FgsParams& p, smem_addr_t luts, smem_addr_t 
 			if (MERGE) nl_s = neighbour_sample<IN16>(raw[q], lane, vl[q], second_half, right_in_picture);
 			else neighbour_samples<IN16>(raw[q], lane, vl[q], vr[q], right_in_picture, nl_s, nr_s);
 			gather_line<IN16, OUT8, MERGE>(L, U, rc, w_cur, w_up, ru, p.bs, raw[q], nl_s, nr_s, w);
-			const bool more = line + kFastLB < nl;
+			const bool more = line + kGatherLB < nl;
 			if (IN16) ld_global_16_if(nxt, raw[q], more && active);
 			else ld_global_8_if(nxt, raw[q], more && active);
 			if (MERGE) {

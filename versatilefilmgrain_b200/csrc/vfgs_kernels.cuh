@@ -187,11 +187,11 @@ fgs_apply_fast_kernel(const __grid_constant__ FgsParams p)
 // per-lane replicated LUT (32 KB, entry = scale | slot byte offset << 8) per gather component, each on a
 // 32 KB boundary, then the general table image (compact LUTs + pattern slots) brought in by one bulk copy.
 #ifndef VFGS_GATHER_THREADS
-#define VFGS_GATHER_THREADS 768
+#define VFGS_GATHER_THREADS 896
 #define VFGS_GATHER_CTAS 1
 #endif
-constexpr int kGatherThreads = VFGS_GATHER_THREADS; // one CTA per SM at up to 80 registers (the gather path carries more per-lane state);
-                                                    // measured ahead of 2 x 384 (one table image per SM) and of 640/704/832 threads
+constexpr int kGatherThreads = VFGS_GATHER_THREADS; // one CTA per SM at up to 72 registers (the gather path carries more per-lane state);
+                                                    // measured ahead of 2 x 384 (one table image per SM) and of 640-832 and 960-1024 threads
 constexpr int kGatherWarps = kGatherThreads / 32;
 
 template <bool IN16, bool OUT8>

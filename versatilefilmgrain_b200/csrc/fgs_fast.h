@@ -153,7 +153,7 @@ inline int lds_s8(smem_addr_t a) { return (int)*(const int8_t*)a; }
 inline int lds_u8(smem_addr_t a) { return (int)*(const uint8_t*)a; }
 #endif
 
-// Measured on B200 (scripts/variant_sweep.sh): with 16-bit output the fast kernel is HBM-bound and runs
+// Measured on B200 (scripts/ab_sweep.sh, -DVFGS_FAST_L1_MODE=0|1|2): with 16-bit output the fast kernel is HBM-bound and runs
 // ~2 % faster when the sample loads allocate in L1 (whole 128-byte lines are brought in ahead of the
 // neighbouring lanes' requests); with 8-bit output it is issue-bound and the streaming operator is ahead.
 #ifndef VFGS_FAST_L1_MODE

@@ -53,8 +53,9 @@ const char* vfgs_b200_last_error(void);
 size_t vfgs_b200_frame_bytes(int width, int height, int depth);
 
 /* nframes packed planar frames already in DEVICE memory; asynchronous on `stream` (a cudaStream_t,
- * NULL = default stream). in == out is allowed when the depths match and every component uses a
- * single pattern; otherwise the buffers must not overlap. */
+ * NULL = default stream). in == out is allowed when the depths match (with sample-adaptive pattern
+ * selection the frames then take a detour through a scratch buffer: two extra passes over the data);
+ * otherwise the buffers must not overlap. */
 int vfgs_b200_add_grain_frames_device(const void* in, void* out, int nframes, int width, int height,
                                       int out_depth, void* stream);
 

@@ -52,6 +52,8 @@ struct Context {
 	Slot slot[kPipeSlots];
 	uint8_t* d_line = nullptr; // compat line path staging
 	size_t line_cap = 0;
+	uint8_t* d_scratch = nullptr; // scratch output of in-place calls with sample-adaptive patterns
+	size_t scratch_cap = 0;
 	int smem_attr = 0;
 	int last_launch[5] = {0, 0, 0, 0, 0};
 	// optional per-launch timing of the grain kernel (vfgs_b200_kernel_timing)
@@ -546,12 +548,46 @@ int vfgs_b200_add_grain_planes_device(const vfgs_b200_planes* in, const vfgs_b20
 	if (int rc = make_geometry(g, width, height, out_depth)) return rc;
 	if (int rc = prepare(-1)) return rc;
 	if (nframes == 0) return VFGS_B200_OK;
-	if (in->y == out->y && (g.in_depth != g.out_depth || !all_uniform()))
-		return set_err(VFGS_B200_ERR_ARG, "in-place needs equal depths and one pattern per component");
+	if (in->y == out->y && g.in_depth != g.out_depth) return set_err(VFGS_B200_ERR_ARG, "in-place needs equal depths");
 	Context& c = g_ctx;
 	cudaStream_t st = (cudaStream_t)stream;
 	if (c.used_stream && c.last_stream != st) CUDA_TRY(cudaStreamSynchronize(c.last_stream)); // d_streams is shared
 	c.last_stream = st; c.used_stream = true;
+	if (in->y == out->y && !all_uniform()) {
+		// In place with sample-adaptive pattern selection: a block's edge filter reads the neighbouring block's
+		// INPUT sample, which another warp may already have overwritten. The frames go through a scratch output
+		// buffer in sub-batches and are copied back (two extra passes over the data; the reference's own
+		// in-place order, block after block along a line, has no such hazard).
+		const size_t fb = g.out_frame_bytes;
+		int per = (int)((256u << 20) / fb);
+		if (per < 1) per = 1;
+		if (per > nframes) per = nframes;
+		if (int rc = grow(c.d_scratch, c.scratch_cap, (size_t)per * fb)) return rc;
+		if (int rc = grow(c.d_streams, c.streams_cap, (size_t)per * g.R * g.spitch * kBlockTableBytes + 16)) return rc;
+		const uint32_t epoch = hw().line_rnd;
+		const size_t ysz = g.ysam * g.out_sample, csz = g.csam * g.out_sample;
+		for (int f0 = 0; f0 < nframes; f0 += per) {
+			const int n = nframes - f0 < per ? nframes - f0 : per;
+			vfgs_b200_planes pi = *in, po;
+			pi.y = (uint8_t*)in->y + (size_t)f0 * in->frame_stride;
+			pi.u = (uint8_t*)in->u + (size_t)f0 * in->frame_stride;
+			pi.v = (uint8_t*)in->v + (size_t)f0 * in->frame_stride;
+			packed_planes(po, c.d_scratch, g, g.out_sample, g.out_frame_bytes);
+			if (int rc = run_frames_device(pi, po, n, g, epoch, (uint64_t)f0, c.d_streams, st)) return rc;
+			for (int f = 0; f < n; f++) { // rows of the caller's planes may be padded: 2-D copies, plane by plane
+				const uint8_t* s = c.d_scratch + (size_t)f * fb;
+				uint8_t* dy = (uint8_t*)out->y + (size_t)(f0 + f) * out->frame_stride;
+				uint8_t* du = (uint8_t*)out->u + (size_t)(f0 + f) * out->frame_stride;
+				uint8_t* dv = (uint8_t*)out->v + (size_t)(f0 + f) * out->frame_stride;
+				const size_t yrow = (size_t)g.width * g.out_sample, crow = (size_t)g.cw * g.out_sample;
+				CUDA_TRY(cudaMemcpy2DAsync(dy, (size_t)out->stride_y, s, yrow, yrow, (size_t)g.height, cudaMemcpyDeviceToDevice, st));
+				CUDA_TRY(cudaMemcpy2DAsync(du, (size_t)out->stride_c, s + ysz, crow, crow, (size_t)g.ch, cudaMemcpyDeviceToDevice, st));
+				CUDA_TRY(cudaMemcpy2DAsync(dv, (size_t)out->stride_c, s + ysz + csz, crow, crow, (size_t)g.ch, cudaMemcpyDeviceToDevice, st));
+			}
+		}
+		advance_registers(g, (uint64_t)nframes);
+		return VFGS_B200_OK;
+	}
 	if (int rc = grow(c.d_streams, c.streams_cap, (size_t)nframes * g.R * g.spitch * kBlockTableBytes + 16)) return rc;
 	if (int rc = run_frames_device(*in, *out, nframes, g, hw().line_rnd, 0, c.d_streams, st)) return rc;
 	advance_registers(g, (uint64_t)nframes);

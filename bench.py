@@ -83,13 +83,20 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.period, self.stop_flag = index, period_s, threading.Event()
         self.sm, self.reasons, self.max_mhz, self.err = [], 0, None, None
-
-    def run(self):
-        try:
+        self.nvml = self.handle = None
+        try:  # NVML is initialised here, before the timed region, so that the thread samples from its first instant
             import pynvml
             pynvml.nvmlInit()
-            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            self.nvml, self.handle = pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # NVML missing: report it, do not invent numbers
+            self.err = repr(e)
+
+    def run(self):
+        if self.handle is None:
+            return
+        pynvml, h = self.nvml, self.handle
+        try:
             while not self.stop_flag.is_set():
                 self.sm.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
                 try:

@@ -309,7 +309,7 @@ def run_b200_arm(args):
     epoch = [int(v) for v in st["lfsr"]]
 
     # resident pool of distinct frames (uniform random codes: worst case for the LUT/pattern gathers)
-    F = args.frames_per_step or int(max(8, min(1024, POOL_INPUT_BYTES // in_bytes)))
+    F = args.frames_per_step or int(max(8, min(4096, POOL_INPUT_BYTES // in_bytes)))
     gen = torch.Generator(device="cuda"); gen.manual_seed(1234 + rank)
     sdt = torch.int16 if depth > 8 else torch.uint8
     if args.data == "uniform":

@@ -49,6 +49,14 @@ struct Context {
 	cudaStream_t last_stream = nullptr;
 	bool used_stream = false;
 	cudaStream_t s_h2d = nullptr, s_k = nullptr, s_d2h = nullptr;
+	// device entry point: the block tables of consecutive calls alternate between two buffers and are computed on a
+	// side stream, so that the table kernel of call k + 1 runs under the grain kernel of call k
+	cudaStream_t s_tab = nullptr;
+	uint32_t* d_tab[2] = {nullptr, nullptr};
+	size_t tab_cap[2] = {0, 0};
+	cudaEvent_t tab_ready[2] = {nullptr, nullptr}, tab_free[2] = {nullptr, nullptr};
+	bool tab_used[2] = {false, false};
+	unsigned tab_next = 0;
 	Slot slot[kPipeSlots];
 	uint8_t* d_line = nullptr; // compat line path staging
 	size_t line_cap = 0;
@@ -143,6 +151,11 @@ int ensure_ctx(int device)
 	CUDA_TRY(cudaStreamCreateWithFlags(&c.s_h2d, cudaStreamNonBlocking));
 	CUDA_TRY(cudaStreamCreateWithFlags(&c.s_k, cudaStreamNonBlocking));
 	CUDA_TRY(cudaStreamCreateWithFlags(&c.s_d2h, cudaStreamNonBlocking));
+	CUDA_TRY(cudaStreamCreateWithFlags(&c.s_tab, cudaStreamNonBlocking));
+	for (int t = 0; t < 2; t++) {
+		CUDA_TRY(cudaEventCreateWithFlags(&c.tab_ready[t], cudaEventDisableTiming));
+		CUDA_TRY(cudaEventCreateWithFlags(&c.tab_free[t], cudaEventDisableTiming));
+	}
 	for (Slot& s : c.slot) {
 		CUDA_TRY(cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
 		CUDA_TRY(cudaEventCreateWithFlags(&s.k_done, cudaEventDisableTiming));
@@ -291,9 +304,10 @@ int launch_apply(const FgsParams& p, cudaStream_t stream, KernelKind kind = kGen
 
 int launch_streams(uint32_t epoch, uint32_t* d_streams, uint16_t* d_woffs, const WoffParams& wp, int nframes, const Geometry& g, uint64_t frame0, cudaStream_t stream)
 {
+	// 128-thread CTAs (4096 registers each) fit beside a resident 768-thread grain CTA
 	const long long warps = (long long)nframes * g.R;
-	const int grid = (int)((warps * 32 + kCtaThreads - 1) / kCtaThreads);
-	lfsr_states_kernel<<<grid, kCtaThreads, 0, stream>>>(epoch, g_ctx.d_pow2, d_streams, d_woffs, wp, nframes, g.R, g.nb, g.spitch, frame0);
+	const int grid = (int)((warps * 32 + kLfsrThreads - 1) / kLfsrThreads);
+	lfsr_states_kernel<<<grid, kLfsrThreads, 0, stream>>>(epoch, g_ctx.d_pow2, d_streams, d_woffs, wp, nframes, g.R, g.nb, g.spitch, frame0);
 	CUDA_TRY(cudaGetLastError());
 	g_launches++;
 	return VFGS_B200_OK;
@@ -317,7 +331,8 @@ void advance_registers(const Geometry& g, uint64_t nframes)
 
 // Streams + grain kernels for `n` frames whose epoch-relative index starts at frame0.
 int run_frames_device(const vfgs_b200_planes& in, const vfgs_b200_planes& out, int n, const Geometry& g,
-                      uint32_t epoch, uint64_t frame0, uint32_t* d_streams, cudaStream_t stream)
+                      uint32_t epoch, uint64_t frame0, uint32_t* d_streams, cudaStream_t stream,
+                      cudaStream_t table_stream = nullptr, cudaEvent_t table_ready = nullptr)
 {
 	FgsParams p;
 	fill_common(p, g);
@@ -344,7 +359,11 @@ int run_frames_device(const vfgs_b200_planes& in, const vfgs_b200_planes& out, i
 	plan_launches(p, g_bi, g_kernel_mode, in.y == out.y, g_ctx.max_smem_optin - 1024, g_ctx.fast_pad, lp);
 	// the register table feeds the general kernel, the window-offset table the fast and gather kernels
 	if (int rc = launch_streams(epoch, lp.any_general ? d_streams : nullptr, (lp.any_fast || lp.any_gather) ? d_woffs : nullptr,
-	                            make_woff_params(p, lp.kind), n, g, frame0, stream)) return rc;
+	                            make_woff_params(p, lp.kind), n, g, frame0, table_stream ? table_stream : stream)) return rc;
+	if (table_stream) { // the tables were computed beside the caller's stream: the grain kernels wait for them
+		CUDA_TRY(cudaEventRecord(table_ready, table_stream));
+		CUDA_TRY(cudaStreamWaitEvent(stream, table_ready, 0));
+	}
 	if (lp.any_fast)
 		if (int rc = launch_apply(lp.fast, stream, kFast)) return rc;
 	if (lp.any_gather)
@@ -588,8 +607,12 @@ int vfgs_b200_add_grain_planes_device(const vfgs_b200_planes* in, const vfgs_b20
 		advance_registers(g, (uint64_t)nframes);
 		return VFGS_B200_OK;
 	}
-	if (int rc = grow(c.d_streams, c.streams_cap, (size_t)nframes * g.R * g.spitch * kBlockTableBytes + 16)) return rc;
-	if (int rc = run_frames_device(*in, *out, nframes, g, hw().line_rnd, 0, c.d_streams, st)) return rc;
+	const int t = (int)(c.tab_next++ & 1u);
+	if (int rc = grow(c.d_tab[t], c.tab_cap[t], (size_t)nframes * g.R * g.spitch * kBlockTableBytes + 16)) return rc;
+	if (c.tab_used[t]) CUDA_TRY(cudaStreamWaitEvent(c.s_tab, c.tab_free[t], 0)); // the grain kernels of two calls ago read this buffer
+	if (int rc = run_frames_device(*in, *out, nframes, g, hw().line_rnd, 0, c.d_tab[t], st, c.s_tab, c.tab_ready[t])) return rc;
+	CUDA_TRY(cudaEventRecord(c.tab_free[t], st));
+	c.tab_used[t] = true;
 	advance_registers(g, (uint64_t)nframes);
 	return VFGS_B200_OK;
 }

@@ -17,6 +17,7 @@
 namespace vfgs {
 
 constexpr int kCtaThreads = 256;
+constexpr int kLfsrThreads = 128; // lfsr_states_kernel
 constexpr int kWarpsPerCta = kCtaThreads / 32;
 
 // ---- mbarrier / bulk-copy PTX -------------------------------------------------------------
@@ -60,7 +61,7 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gm
 // uint32[64][32]; lane i owns output bit i, a ballot assembles the word), then walk the row 32 steps
 // at a time: consecutive blocks are consecutive 32-bit windows of one bit-stream, so lane l takes
 // window l of every {word k, word k+1} pair and the 32 registers go out as one coalesced store.
-__global__ void __launch_bounds__(kCtaThreads)
+__global__ void __launch_bounds__(kLfsrThreads)
 lfsr_states_kernel(uint32_t epoch_state, const uint32_t* __restrict__ pow2, uint32_t* __restrict__ states,
                    uint16_t* __restrict__ woffs, const WoffParams wp,
                    int nframes, int R, int nb, int spitch, unsigned long long frame0)

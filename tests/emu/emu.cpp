@@ -156,3 +156,57 @@ extern "C" int emu_add_grain_frames(const void* state, const void* in, void* out
 			for (int lane = 0; lane < 32; lane++) process_task(lp.general, tab, (uint32_t)task, lane);
 	return (lp.any_fast ? 1 : 0) | (lp.any_general ? 2 : 0) | (lp.any_gather ? 4 : 0);
 }
+
+// Launch planning of a whole-frame call, without running anything (host logic only): which kernel serves each
+// component, the fast kernel's shared-memory layout and lane-unit width. out (ints): kind[3], fsmem, fpad,
+// fimg_off[3], fimg_bytes[3], fwide[3], funits_per_row[3], gather_smem.
+extern "C" void emu_plan(const void* state, int width, int height, int out_depth, int in_place, int mode, int* out)
+{
+	const StateDump& d = *(const StateDump*)state;
+	HwState h;
+	memcpy(h.pattern, d.pattern, sizeof(h.pattern));
+	memcpy(h.slut, d.slut, sizeof(h.slut));
+	memcpy(h.plut, d.plut, sizeof(h.plut));
+	h.rnd = d.rnd; h.rnd_up = d.rnd_up; h.line_rnd = d.line_rnd; h.line_rnd_up = d.line_rnd_up;
+	h.scale_shift = d.scale_shift; h.bs = d.bs;
+	h.y_min = d.y_min; h.y_max = d.y_max; h.c_min = d.c_min; h.c_max = d.c_max;
+	h.csubx = d.csubx; h.csuby = d.csuby;
+	const int in_depth = 8 + h.bs;
+	if (!out_depth) out_depth = in_depth;
+	const int cw = width / h.csubx, ch = height / h.csuby;
+	const size_t isz = in_depth > 8 ? 2 : 1, osz = out_depth > 8 ? 2 : 1;
+	const size_t ysam = (size_t)width * height, csam = (size_t)cw * ch;
+	TableInfo bi;
+	std::vector<uint8_t> blob, fblob;
+	build_tables(h, bi, blob, fblob);
+	FgsParams p;
+	memset(&p, 0, sizeof(p));
+	fill_state_params(p, h, bi);
+	p.nframes = 1; p.nb = (width + 15) / 16; p.R = (height + 15) / 16; p.row_begin = 0; p.rows = p.R;
+	p.y_begin = 0; p.y_end = height;
+	p.in_bytes = (int)isz; p.out_bytes = (int)osz;
+	p.in_frame_bytes = (long long)((ysam + 2 * csam) * isz);
+	p.out_frame_bytes = (long long)((ysam + 2 * csam) * osz);
+	static uint8_t* const base_in = (uint8_t*)0x10000000, * const base_out = (uint8_t*)0x40000000; // aligned dummies, never dereferenced
+	const size_t off[3] = {0, ysam, ysam + csam};
+	for (int c = 0; c < 3; c++) {
+		p.comp[c].in = base_in + off[c] * isz;
+		p.comp[c].out = (in_place ? base_in : base_out) + off[c] * osz;
+		p.comp[c].in_row_bytes = (long long)((c ? cw : width) * isz);
+		p.comp[c].out_row_bytes = (long long)((c ? cw : width) * osz);
+		p.comp[c].width = c ? cw : width;
+		p.comp[c].lines = c ? ch : height;
+	}
+	p.spitch = p.nb + 2; p.stream_rows = p.R;
+	finish_tasks(p);
+	LaunchPlan lp;
+	plan_launches(p, bi, mode, in_place != 0, 227 * 1024, kLutAlign - 1152, lp);
+	int k = 0;
+	for (int c = 0; c < 3; c++) out[k++] = lp.kind[c];
+	out[k++] = lp.fast.fsmem; out[k++] = lp.fast.fpad;
+	for (int c = 0; c < 3; c++) out[k++] = lp.fast.fimg_off[c];
+	for (int c = 0; c < 3; c++) out[k++] = lp.fast.fimg_bytes[c];
+	for (int c = 0; c < 3; c++) out[k++] = lp.fast.fwide[c];
+	for (int c = 0; c < 3; c++) out[k++] = lp.fast.funits_per_row[c];
+	out[k++] = lp.gather_smem;
+}

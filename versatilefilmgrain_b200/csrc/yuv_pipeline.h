@@ -34,6 +34,7 @@ struct Pipe {
 	unsigned long long frames_done = 0, flushes = 0;
 	double t_read = 0, t_gpu = 0, t_write = 0; // seconds spent in fread, in the grain calls, in fwrite
 	double t_ctx = 0, t_alloc = 0, t_wait = 0; // CUDA context creation, page-locked allocation, caller waiting for the worker
+	~Pipe() { if (worker.joinable()) worker.join(); } // a caller that exits without yuv_free must not trip std::terminate
 } g_pipe;
 
 double pipe_now()

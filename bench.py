@@ -176,6 +176,12 @@ class CpuArm:
         self.pool.map(_cpu_worker_step, range(self.cores), chunksize=1)
         return time.perf_counter() - t0
 
+    def step_one_core(self):
+        """The same work on a single worker while the others idle: the reference as it ships (one thread)."""
+        t0 = time.perf_counter()
+        self.pool.map(_cpu_worker_step, range(1), chunksize=1)
+        return time.perf_counter() - t0
+
     def close(self):
         self.pool.close()
         self.pool.join()
@@ -268,9 +274,11 @@ def run_b200_arm(args):
         arm = CpuArm(args.workload, fpw)
         arm.step()
         tt = [arm.step() for _ in range(3)]
+        t1 = arm.step_one_core()
         arm.close()
         cpu_baseline = {"value": arm.cores * fpw * len(tt) / sum(tt), "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
-                        "sample": arm.describe() + f"; {len(tt)} timed steps after 1 warm-up"}
+                        "sample": arm.describe() + f"; {len(tt)} timed steps after 1 warm-up",
+                        "one_core": {"value": fpw / t1, "unit": UNIT, "what": "one worker alone (the reference is single-threaded), 1 step"}}
 
     placement = bind_to_gpu_numa_node(local) if world > 1 else "single rank, not bound"
     torch.cuda.set_device(local)

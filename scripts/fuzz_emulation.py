@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""Fuzzes the kernels' task code (host build, tests/emu) against the oracle: random hardware states programmed
+through the setters (depth, format, 1-8 pattern slots per bank, legal range, scale shift, -128 pattern bytes),
+random picture sizes, in-range and garbage samples, every kernel-selection mode. Test tool, no GPU.
+
+    python scripts/fuzz_emulation.py [seed] [seconds]
+
+(Found in round 1: a Cr component with its own fast-kernel image next to a sample-adaptive Cb got an empty image.)"""
+import ctypes as C
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+
+from oracle.pyoracle import RefState, _ptr  # noqa: E402
+from tests.util import Oracle, build_emu, first_mismatch, program_random_state, synth_frames  # noqa: E402
+
+WIDTHS = [136, 144, 152, 160, 200, 256, 264, 272, 512, 520, 528, 1040]
+
+
+def one_case(emu, rng):
+    depth = int(rng.choice([8, 10])); fmt = str(rng.choice(["420", "422", "444"]))
+    spec = (int(rng.integers(1, 1 << 30)), depth, fmt, int(rng.integers(1, 9)), int(rng.integers(1, 9)),
+            int(rng.integers(0, 2)), int(rng.integers(2, 8)), bool(rng.integers(0, 4) == 0))
+    w = int(rng.choice(WIDTHS)); h = max(2, int(rng.integers(1, 70))); n = int(rng.integers(1, 4))
+    for od in ((0, 8) if depth == 10 else (0,)):
+        frames = synth_frames(n, w, h, fmt, depth, seed=spec[0] % 1000)
+        if depth == 10 and rng.integers(0, 3) == 0:
+            frames = rng.integers(0, 65536, size=frames.size, dtype=np.uint16)  # codes far outside 10 bits
+        o = Oracle(); program_random_state(o, *spec)
+        st = RefState(); o.L.oracle_get_state(o.h, C.byref(st))
+        outs = []
+        for mode in (0, 1, 2):
+            out = np.zeros(frames.shape, dtype=np.uint8 if (od == 8 or depth == 8) else np.uint16)
+            emu.emu_add_grain_frames(C.byref(st), _ptr(frames), _ptr(out), n, w, h, od, 0, mode)
+            outs.append(out)
+        want = o.add_grain_frames(frames, n, w, h, od)
+        for mode, got in enumerate(outs):
+            if not np.array_equal(got, want):
+                return f"MISMATCH spec={spec} w={w} h={h} n={n} od={od} mode={mode}: {first_mismatch(got, want, w, h, fmt, n)}"
+    return None
+
+
+def run(seed: int, seconds: float, max_cases: int = 0):
+    emu = C.CDLL(build_emu())
+    emu.emu_add_grain_frames.argtypes = [C.c_void_p] * 3 + [C.c_int] * 6
+    rng = np.random.default_rng(seed)
+    t0, n = time.time(), 0
+    while time.time() - t0 < seconds and (max_cases == 0 or n < max_cases):
+        bad = one_case(emu, rng)
+        if bad:
+            return n, bad
+        n += 1
+    return n, None
+
+
+if __name__ == "__main__":
+    n, bad = run(int(sys.argv[1]) if len(sys.argv) > 1 else 0, float(sys.argv[2]) if len(sys.argv) > 2 else 60)
+    print(bad or f"fuzz ok: {n} cases")
+    sys.exit(1 if bad else 0)

@@ -53,3 +53,15 @@ def test_emulated_kernels_on_random_states(emu, spec):
             want = o.add_grain_frames(frames, n, w, h, od)
             for mode, got in enumerate(outs):
                 assert np.array_equal(got, want), (spec, w, h, od, mode, first_mismatch(got, want, w, h, fmt, n))
+
+
+def test_short_fuzz_of_the_emulated_kernels():
+    """A few hundred random (state, size, samples) cases through every kernel's task code (scripts/fuzz_emulation.py runs
+    the same generator for as long as wanted)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("fuzz_emulation", os.path.join(os.path.dirname(__file__), "..", "scripts", "fuzz_emulation.py"))
+    fuzz = importlib.util.module_from_spec(spec); spec.loader.exec_module(fuzz)
+    n, bad = fuzz.run(seed=2026, seconds=20, max_cases=400)
+    assert bad is None, bad
+    assert n > 50

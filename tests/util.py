@@ -96,4 +96,6 @@ RANDOM_STATES = [
     (1, 8, "422", 1, 1, 0, 2, False), (2, 8, "444", 1, 1, 1, 7, False), (3, 8, "444", 3, 2, 0, 4, False),
     (4, 10, "422", 1, 4, 1, 3, False), (5, 10, "444", 8, 8, 0, 6, False), (6, 10, "420", 2, 1, 0, 2, False),
     (7, 10, "420", 1, 1, 1, 7, True), (8, 8, "420", 5, 3, 0, 5, True), (9, 10, "444", 1, 1, 0, 5, False),
+    # found by fuzzing the emulated kernels: Cb sample-adaptive (gather kernel), Cr one slot (fast kernel, own image)
+    (6605739, 10, "422", 4, 2, 0, 7, False), (765400224, 10, "444", 6, 2, 1, 5, False),
 ]

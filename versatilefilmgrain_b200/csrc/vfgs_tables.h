@@ -50,6 +50,7 @@ struct TableInfo {
 	// slot has no -128 byte (so that -pattern fits int8)
 	bool fast_ok[3];
 	int fimg_src[3], fimg_bytes[3]; // component images inside the fast image (bytes 0 when !fast_ok)
+	bool fshare_cbcr;               // Cr reads Cb's image (same pattern slot)
 	int fpat_off[3][2], fpat_stride[3], fpat_copy[3], fbytes; // fpat_off: relative to the component image; fpat_copy: bytes from one column-shifted copy to the next
 };
 
@@ -93,6 +94,7 @@ inline void build_tables(const HwState& h, TableInfo& g_bi, std::vector<uint8_t>
 	// fast_copies() column-shifted copies (copy k holds the pattern moved left by k * 8 / copies bytes), so that
 	// every window column has a copy in which it sits on an 8-byte boundary (fgs_fast.h, window_offset)
 	int off = 256 * 4;
+	g_bi.fshare_cbcr = false;
 	for (int c = 0; c < 3; c++) {
 		const int rows = c ? crows : 64, cols = c ? ccols : 64;
 		const int ncopy = fast_copies((c && h.csubx > 1) ? 8 : 16);
@@ -111,15 +113,19 @@ inline void build_tables(const HwState& h, TableInfo& g_bi, std::vector<uint8_t>
 		g_bi.fpat_off[c][1] = ncopy * rows * pitch;
 		g_bi.fimg_src[c] = off;
 		g_bi.fimg_bytes[c] = ok ? 2 * ncopy * rows * pitch : 0;
-		if (c == 2 && ok && g_bi.fast_ok[1] && g_bi.uniform_pi[1] == slot) g_bi.fimg_src[2] = g_bi.fimg_src[1]; // Cb and Cr read the same slot: one image
-		else off += g_bi.fimg_bytes[c];
+		if (c == 2 && ok && g_bi.fast_ok[1] && g_bi.uniform_pi[1] == slot) { // Cb and Cr read the same slot: one image
+			g_bi.fimg_src[2] = g_bi.fimg_src[1];
+			g_bi.fshare_cbcr = true;
+		} else {
+			off += g_bi.fimg_bytes[c];
+		}
 	}
 	g_bi.fbytes = (off + 15) & ~15;
 	g_fblob.assign((size_t)g_bi.fbytes, 0);
 	uint32_t* clut = (uint32_t*)g_fblob.data();
 	for (int i = 0; i < 256; i++) clut[i] = (uint32_t)h.slut[0][i] | ((uint32_t)h.slut[1][i] << 8) | ((uint32_t)h.slut[2][i] << 16);
 	for (int c = 0; c < 3; c++) {
-		if (!g_bi.fast_ok[c] || (c == 2 && g_bi.fimg_src[2] == g_bi.fimg_src[1])) continue;
+		if (!g_bi.fast_ok[c] || (c == 2 && g_bi.fshare_cbcr)) continue;
 		const int rows = c ? crows : 64, cols = c ? ccols : 64;
 		const int ncopy = fast_copies((c && h.csubx > 1) ? 8 : 16), shift = 8 / ncopy;
 		for (int k = 0; k < ncopy; k++) {
@@ -192,7 +198,7 @@ inline void place_fast_images(FgsParams& p, const TableInfo& bi, int pad, const 
 		const int n = p.fimg_bytes[c];
 		p.fimg_off[c] = 0;
 		if (!n) continue;
-		if (c == 2 && p.fimg_bytes[1] && p.fimg_src[2] == p.fimg_src[1]) { // shares Cb's image: nothing to copy
+		if (c == 2 && bi.fshare_cbcr && p.fimg_bytes[1]) { // shares Cb's image (and Cb's is resident): nothing to copy
 			p.fimg_off[2] = p.fimg_off[1]; p.fimg_bytes[2] = 0;
 			continue;
 		}

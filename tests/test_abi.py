@@ -131,3 +131,49 @@ def test_frame_api_rejects_bad_arguments_without_touching_a_gpu(hw_lib):
     assert L.vfgs_b200_add_grain_frames_device(p, p, 1, 256, 64, 10, None) == 1  # out depth > in depth
     assert b"out_depth" in L.vfgs_b200_last_error()
     assert L.vfgs_b200_add_grain_frames_host(None, p, 1, 256, 64, 0) == 1
+
+
+def test_random_setter_sequences_match_the_reference(hw_lib):
+    """Random interleavings of every vfgs_hw.h setter (the state machine is order-dependent: scale_shift follows the
+    depth in force, chroma patterns are repacked with the subsampling in force) leave the shim's mirror, the oracle
+    and, where it is mounted, the live reference in the same state."""
+    from oracle import pyoracle
+    from tests.util import states_equal
+    ref = None
+    if pyoracle.have_reference():
+        ref = pyoracle.Reference()
+    rng = np.random.default_rng(77)
+    for trial in range(40):
+        hw_lib.reset()
+        o = Oracle()
+        targets = [hw_lib, o]
+        if ref is not None:
+            ref.reset()
+            targets.append(ref)
+        for _ in range(int(rng.integers(5, 40))):
+            op = int(rng.integers(0, 9))
+            if op == 0:
+                args = ("vfgs_set_depth", (int(rng.choice([8, 10])),))
+            elif op == 1:
+                sx, sy = [(2, 2), (2, 1), (1, 1), (1, 2)][int(rng.integers(0, 4))]
+                args = ("vfgs_set_chroma_subsampling", (sx, sy))
+            elif op == 2:
+                args = ("vfgs_set_scale_shift", (int(rng.integers(2, 8)),))
+            elif op == 3:
+                args = ("vfgs_set_legal_range", (int(rng.integers(0, 2)),))
+            elif op == 4:
+                args = ("vfgs_set_seed", (int(rng.integers(0, 1 << 32)),))
+            elif op == 5:
+                args = ("vfgs_set_luma_pattern", (int(rng.integers(0, 8)), rng.integers(-128, 128, size=(64, 64), dtype=np.int8)))
+            elif op == 6:
+                args = ("vfgs_set_chroma_pattern", (int(rng.integers(0, 8)), rng.integers(-128, 128, size=(64, 64), dtype=np.int8)))
+            elif op == 7:
+                args = ("vfgs_set_scale_lut", (int(rng.integers(0, 3)), rng.integers(0, 256, size=256, dtype=np.uint8)))
+            else:
+                args = ("vfgs_set_pattern_lut", (int(rng.integers(0, 3)), (rng.integers(0, 8, size=256).astype(np.uint8) << 4)))
+            for t in targets:
+                getattr(t, args[0])(*args[1])
+        want = o.state()
+        assert states_equal(hw_lib.state(), want) == [], trial
+        if ref is not None:
+            assert states_equal(ref.state(), want) == [], trial

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Fuzzes the kernels' task code (host build, tests/emu) against the oracle: random hardware states programmed
 through the setters (depth, format, 1-8 pattern slots per bank, legal range, scale shift, -128 pattern bytes),
-random picture sizes, in-range and garbage samples, every kernel-selection mode. Test tool, no GPU.
+random picture sizes, in-range and garbage samples, frame offsets into a running sequence, in-place operation, every
+kernel-selection mode. Test tool, no GPU.
 
     python scripts/fuzz_emulation.py [seed] [seconds]
 
@@ -23,7 +24,8 @@ WIDTHS = [136, 144, 152, 160, 200, 256, 264, 272, 512, 520, 528, 1040]
 
 def one_case(emu, rng):
     depth = int(rng.choice([8, 10])); fmt = str(rng.choice(["420", "422", "444"]))
-    spec = (int(rng.integers(1, 1 << 30)), depth, fmt, int(rng.integers(1, 9)), int(rng.integers(1, 9)),
+    one = rng.integers(0, 4) == 0  # a quarter of the cases with one pattern per bank (fast kernel everywhere)
+    spec = (int(rng.integers(1, 1 << 30)), depth, fmt, 1 if one else int(rng.integers(1, 9)), 1 if one else int(rng.integers(1, 9)),
             int(rng.integers(0, 2)), int(rng.integers(2, 8)), bool(rng.integers(0, 4) == 0))
     w = int(rng.choice(WIDTHS)); h = max(2, int(rng.integers(1, 70))); n = int(rng.integers(1, 4))
     for od in ((0, 8) if depth == 10 else (0,)):
@@ -32,15 +34,21 @@ def one_case(emu, rng):
             frames = rng.integers(0, 65536, size=frames.size, dtype=np.uint16)  # codes far outside 10 bits
         o = Oracle(); program_random_state(o, *spec)
         st = RefState(); o.L.oracle_get_state(o.h, C.byref(st))
+        first = int(rng.integers(0, 5000)) if rng.integers(0, 3) == 0 else 0  # frames of a sequence already under way
         outs = []
         for mode in (0, 1, 2):
             out = np.zeros(frames.shape, dtype=np.uint8 if (od == 8 or depth == 8) else np.uint16)
-            emu.emu_add_grain_frames(C.byref(st), _ptr(frames), _ptr(out), n, w, h, od, 0, mode)
-            outs.append(out)
+            emu.emu_add_grain_frames(C.byref(st), _ptr(frames), _ptr(out), n, w, h, od, first, mode)
+            outs.append((f"mode={mode}", out))
+        if spec[3] == 1 and spec[4] == 1 and od == 0:  # one pattern per component: in place as well
+            buf = frames.copy()
+            emu.emu_add_grain_frames(C.byref(st), _ptr(buf), _ptr(buf), n, w, h, od, first, 0)
+            outs.append(("in place", buf))
+        o.skip_frames(first, w, h)
         want = o.add_grain_frames(frames, n, w, h, od)
-        for mode, got in enumerate(outs):
+        for what, got in outs:
             if not np.array_equal(got, want):
-                return f"MISMATCH spec={spec} w={w} h={h} n={n} od={od} mode={mode}: {first_mismatch(got, want, w, h, fmt, n)}"
+                return f"MISMATCH spec={spec} w={w} h={h} n={n} od={od} first={first} {what}: {first_mismatch(got, want, w, h, fmt, n)}"
     return None
 
 

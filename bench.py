@@ -3,9 +3,16 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
 
-One "step" is one pass of the hot path over one batch of synthetic frames of the workload's size
-(default: the BASELINE.json headline, 3840x2160 10-bit 4:2:0). The batch is a pool of distinct
-frames several GB large, so every step streams from and to HBM (inputs larger than L2).
+One "step" is one batch of synthetic frames of the workload's size through the hot path (default: the
+BASELINE.json headline, 3840x2160 10-bit 4:2:0): PASSES calls of the C-ABI device entry point, each over
+a resident pool of distinct frames several GB large (inputs larger than L2, so every call streams from and
+to HBM), with the frame index -- hence the LFSR state -- running on from call to call. PASSES is sized so
+that a step moves ~400 GB (about 65 ms on one B200): the default 20 steps time more than a second.
+
+  --total-frames T   strong scaling (BASELINE.json configs[4]: --workload 8k420_ff_test1 --total-frames 2400):
+             a step is the WHOLE job of T frames; rank r owns the contiguous shard shard_range(T, r, N), jumps
+             to its first frame (vfgs_b200_skip_frames) and cycles its resident pool while the frame index
+             runs over the shard. "scaling": "strong".
 
   value      frames/s, device-resident (inputs already in HBM), CUDA events on the launching stream,
              max over ranks; whole job over all N GPUs
@@ -18,8 +25,11 @@ frames several GB large, so every step streams from and to HBM (inputs larger th
   --impl reference  times that CPU implementation instead of the CUDA path (rank 0 only)
 
 Multi-GPU: one process per GPU (torchrun). Frames are sharded: every rank owns a contiguous run of
-each step's global batch and derives its LFSR start state by jump-ahead; there is no collective on
-the data path (NCCL is used only for the barrier and the max-over-ranks of the timings).
+each call's global batch (weak scaling, default) or of the whole job (--total-frames) and derives its LFSR
+start state by jump-ahead; there is no collective on the data path (NCCL is used only for the barrier and
+the max-over-ranks of the timings). Before anything is timed every rank reproduces reference digests at
+NON-ZERO frame offsets (tests/golden "shards": groups g = rank, rank + N, ... of the reference's
+continuous run), so a wrong shard start cannot go unnoticed.
 """
 from __future__ import annotations
 
@@ -217,7 +227,7 @@ def run_reference_arm(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic", "impl": "reference",
-        "config": workload_config(args.workload, arm.cores * fpw, "cpu: frames stay in host memory"),
+        "config": workload_config(args.workload), "frames_per_step": arm.cores * fpw,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": arm.describe()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -225,11 +235,13 @@ def run_reference_arm(args):
     return 0
 
 
-def workload_config(name, frames_per_step, l2_note):
+def workload_config(name):
+    """Identical in both arms (the driver compares the dicts); per-arm quantities are top-level keys of the line."""
     case, w, h, fmt, depth, od = WORKLOADS[name]
     return {"workload": f"{w}x{h} {depth}-bit {fmt[0]}:{fmt[1]}:{fmt[2]} -> {od or depth}-bit, grain config {case.split('|')[0]}"
                         f"{' gain ' + case.split('|g')[1] if not case.endswith('g100') else ''}, uniform random samples",
-            "name": name, "frames_per_step": frames_per_step, "l2": l2_note}
+            "name": name,
+            "l2": "inputs larger than L2: every call streams a resident pool of distinct frames (GBs, >> 126 MB L2) once"}
 
 
 # ------------------------------------------------------------------------------------- CUDA arm
@@ -252,6 +264,51 @@ def bind_to_gpu_numa_node(index: int):
         return f"not bound ({type(e).__name__})"
 
 
+def parity_gate(hw, G, case, fmt, depth, od, rank, world):
+    """Before anything is timed: the workload's grain configuration on golden inputs must reproduce the digests
+    the unmodified reference produced (tests/golden/golden.npz). Every rank does the plain golden cases and, from
+    the reference's continuous multi-group run ("shards"), the groups g = rank, rank + world, ...: each of those
+    starts at a non-zero frame offset reached by jump-ahead, which is exactly what a shard start is.
+    Returns (checks done, error text or None)."""
+    import torch
+    from tests.fixtures import parse_output_key, program_case, sha, synth_frames
+    from versatilefilmgrain_b200.sharding import position_shard
+    meta = G.cases[case]
+    epoch = [int(v) for v in G.state(case)["lfsr"]]
+
+    def run(frames, n, w, h, first):
+        hw.reset()
+        program_case(hw, G, case)
+        position_shard(hw, epoch, first, w, h)
+        d_s = torch.from_numpy(frames.view(np.int16) if depth > 8 else frames).cuda()
+        d_o = torch.zeros(frames.size, dtype=torch.int16 if (od or depth) > 8 else torch.uint8, device="cuda")
+        hw.add_grain_frames_device(d_s, d_o, n, w, h, od)
+        torch.cuda.synchronize()
+        got = d_o.cpu().numpy()
+        return got.view(np.uint16) if (od or depth) > 8 else got
+
+    done = 0
+    for key, want in meta["outputs"].items():
+        gw, gh, gn, gseed, god = parse_output_key(key)
+        if god != od:
+            continue
+        got = run(synth_frames(gn, gw, gh, fmt, depth, seed=gseed), gn, gw, gh, 0)
+        if sha(got) != want["sha256"] or hw.get_lfsr() != want["lfsr_after"]:
+            return done, f"golden {key}: CUDA output differs from the reference digest"
+        done += 1
+    for key, groups in meta["shards"].items():
+        gw, gh, gn, gseed, god = parse_output_key(key)
+        if god != od:
+            continue
+        frames = synth_frames(gn, gw, gh, fmt, depth, seed=gseed)
+        for g in range(rank % len(groups), len(groups), world):
+            got = run(frames, gn, gw, gh, g * gn)
+            if sha(got) != groups[g]["sha256"] or hw.get_lfsr() != groups[g]["lfsr_after"]:
+                return done, f"shard start at frame {g * gn} of {key}: CUDA output differs from the reference digest"
+            done += 1
+    return done, None
+
+
 def run_b200_arm(args):
     import torch
     import torch.distributed as dist
@@ -268,8 +325,9 @@ def run_b200_arm(args):
         return subprocess.call(cmd)
     case, w, h, fmt, depth, od = WORKLOADS[args.workload]
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        # timed first, before this process creates a CUDA context (the workers are forked)
+    if rank == 0 and not args.no_cpu_baseline:
+        # timed first, before this process creates a CUDA context (the workers are forked); with several ranks the
+        # others wait in init_process_group meanwhile
         fpw = cpu_frames_per_worker(w, h)
         arm = CpuArm(args.workload, fpw)
         arm.step()
@@ -285,39 +343,36 @@ def run_b200_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    from tests.fixtures import load_golden, parse_output_key, program_case, sha, synth_frames  # nothing from oracle/ here
+    from tests.fixtures import load_golden, program_case  # nothing from oracle/ here
     from versatilefilmgrain_b200 import VfgsHw
-    from versatilefilmgrain_b200.sharding import position_shard
+    from versatilefilmgrain_b200.sharding import position_shard, shard_range
 
     samples, in_bytes, out_bytes = frame_geometry(w, h, fmt, depth, od)
     G = load_golden()
     hw = VfgsHw(device=local)
 
-    # parity gate: the workload's grain configuration on the golden input must
-    # reproduce the digest the unmodified reference produced (tests/golden/golden.npz) before anything is timed
-    for key, want in G.cases[case]["outputs"].items():
-        gw, gh, gn, gseed, god = parse_output_key(key)
-        if god != od:
-            continue
-        hw.reset()
-        program_case(hw, G, case)
-        frames = synth_frames(gn, gw, gh, fmt, depth, seed=gseed)
-        d_s = torch.from_numpy(frames.view(np.int16) if depth > 8 else frames).cuda()
-        d_o = torch.zeros(frames.size, dtype=torch.int16 if (od or depth) > 8 else torch.uint8, device="cuda")
-        hw.add_grain_frames_device(d_s, d_o, gn, gw, gh, od)
-        torch.cuda.synchronize()
-        got = d_o.cpu().numpy()
-        got = got.view(np.uint16) if (od or depth) > 8 else got
-        if sha(got) != want["sha256"] or hw.get_lfsr() != want["lfsr_after"]:
-            print(json.dumps({"error": "parity gate failed: CUDA output differs from the reference digest", "workload": args.workload, "golden": key}), flush=True)
-            return 2
-        del d_s, d_o
+    checks, err = parity_gate(hw, G, case, fmt, depth, od, rank, world)
+    bad = torch.tensor([1 if err else 0], dtype=torch.int32, device="cuda")
+    if world > 1:
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+    if err:
+        print(json.dumps({"error": "parity gate failed: " + err, "workload": args.workload, "rank": rank}), flush=True)
+    if int(bad.item()):
+        return 2
     hw.reset()
     st = program_case(hw, G, case)
     epoch = [int(v) for v in st["lfsr"]]
 
     # resident pool of distinct frames (uniform random codes: worst case for the LUT/pattern gathers)
     F = args.frames_per_step or int(max(8, min(4096, POOL_INPUT_BYTES // in_bytes)))
+    strong = args.total_frames > 0
+    if strong:
+        my_first, my_count = shard_range(args.total_frames, rank, world)
+        F = max(1, min(F, (args.total_frames + world - 1) // world))
+        passes = None
+    else:
+        # calls per step: ~400 GB of algorithmic traffic per step and GPU, so that 20 steps time > 1 s
+        passes = args.passes or max(1, int(round(4.0e11 / (F * (in_bytes + out_bytes)))))
     gen = torch.Generator(device="cuda"); gen.manual_seed(1234 + rank)
     sdt = torch.int16 if depth > 8 else torch.uint8
     if args.data == "uniform":
@@ -343,9 +398,19 @@ def run_b200_arm(args):
     stream = torch.cuda.current_stream()
 
     def step(s):
-        # rank r owns frames [r*F, (r+1)*F) of step s's global batch of world*F frames
-        position_shard(hw, epoch, (s * world + rank) * F, w, h)
-        hw.add_grain_frames_device(src, dst, F, w, h, od, stream)
+        if strong:
+            # the whole job: this rank's contiguous shard, the pool cycled while the frame index runs over the shard
+            done = 0
+            while done < my_count:
+                n = min(F, my_count - done)
+                position_shard(hw, epoch, my_first + done, w, h)
+                hw.add_grain_frames_device(src, dst, n, w, h, od, stream)
+                done += n
+        else:
+            # call p of step s: rank r owns frames [r*F, (r+1)*F) of that call's global batch of world*F frames
+            for p in range(passes):
+                position_shard(hw, epoch, ((s * passes + p) * world + rank) * F, w, h)
+                hw.add_grain_frames_device(src, dst, F, w, h, od, stream)
 
     def barrier():
         torch.cuda.synchronize()
@@ -374,7 +439,9 @@ def run_b200_arm(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    value = world * F * args.steps / (ms_max * 1e-3)
+    frames_per_step = args.total_frames if strong else world * F * passes  # whole job, all ranks
+    my_frames_per_step = my_count if strong else F * passes
+    value = frames_per_step * args.steps / (ms_max * 1e-3)
 
     # end to end through the host entry point: pinned host buffers, H2D + kernels + D2H timed
     Fe = min(F, args.e2e_frames or int(max(8, min(128, 2.4e9 // in_bytes))))
@@ -383,7 +450,7 @@ def run_b200_arm(args):
     h_out = torch.empty(Fe * samples, dtype=dst.dtype).pin_memory()
     del src, dst
     torch.cuda.empty_cache()
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, min(args.steps, 20))
     for s in range(2):
         hw.add_grain_frames_host(h_in, h_out, Fe, w, h, od)
     barrier()
@@ -421,26 +488,33 @@ def run_b200_arm(args):
     del d_in, d_out
 
     peak, peak_src = measured_peak_gbs()
+    # the grain kernels of one C-ABI call (one launch for single-pattern configs, two when components split between
+    # the fast and the gather kernel) move the call's algorithmic bytes: bytes of all calls / their summed device time
+    my_algo_bytes = my_frames_per_step * args.steps * (in_bytes + out_bytes)
+    achieved = my_algo_bytes / (k_ms * 1e-3) / 1e9 if k_n else None
+    calls_per_step = (k_n / max(args.steps, 1)) / max(1, len(hw.last_launch()["kernels"]))
+    frames_per_call = my_frames_per_step / max(calls_per_step, 1e-9)
     traffic = traffic_src = None
     try:  # DRAM bytes per frame of the grain kernel from the committed ncu capture of this workload
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            t = json.load(f).get(args.workload) or {}
-        if t.get("dram_bytes_per_frame") and args.data == "uniform":
-            traffic, traffic_src = t["dram_bytes_per_frame"] * F, t["source"]
+            tj = json.load(f).get(args.workload) or {}
+        if tj.get("dram_bytes_per_frame") and args.data == "uniform":
+            traffic = tj["dram_bytes_per_frame"] * frames_per_call
+            traffic_src = (f"{tj['source']}: dram__bytes_read.sum + dram__bytes_write.sum per frame of that capture, "
+                           f"scaled to the {frames_per_call:.0f} frames of one call here")
     except Exception:
         pass
-    algo_bytes = F * (in_bytes + out_bytes)
-    # grain kernels of one step (one launch for single-pattern configs, two when components split
-    # between the fast and the gather kernel): algorithmic bytes of the step / their summed device time
-    achieved = algo_bytes / (k_ms / args.steps * 1e-3) / 1e9 if k_n else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic" if args.data == "uniform" else "synthetic (smooth gradient + noise)",
-        "config": workload_config(args.workload, F, f"inputs larger than L2: resident pool {F * (in_bytes + out_bytes) / 1e9:.1f} GB per GPU streamed once per step"),
+        "config": workload_config(args.workload),
+        "frames_per_step": frames_per_step, "frames_per_call_per_gpu": frames_per_call,
+        "pool_gb_per_gpu": F * (in_bytes + out_bytes) / 1e9,
+        "timed_region_s": ms_max * 1e-3,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": Fe * in_bytes, "d2h_bytes_per_step": Fe * out_bytes,
-                "frames_per_step": Fe, "steps": e2e_steps, "host_buffers": "pinned", "cpu_placement": placement,
+                "frames_per_step": Fe, "steps": e2e_steps, "host_buffers": "pinned", "cpu_placement": placement, "scaling": "weak",
                 "gbs_each_way": [e2e_value * in_bytes / 1e9, e2e_value * out_bytes / 1e9],
                 "pcie_copies_alone": {"value": copy_only_value, "unit": UNIT,
                                       "what": "the same H2D and D2H copies without kernels, concurrently, all ranks: the box's PCIe ceiling for this step"}},
@@ -448,13 +522,18 @@ def run_b200_arm(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "kernel": "+".join(hw.last_launch()["kernels"]), "launches_per_step": k_n / max(args.steps, 1),
-                     "bytes_per_launch": algo_bytes, "avg_launch_ms": (k_ms / args.steps) if k_n else None,
+                     "bytes_per_launch": frames_per_call * (in_bytes + out_bytes),
+                     "avg_launch_ms": (k_ms / max(calls_per_step * args.steps, 1e-9)) if k_n else None,
                      "kernel_share_of_step": (k_ms / ms) if ms else None,
                      "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None},
         "bytes_per_frame": in_bytes + out_bytes,
         "device_resident_gbs": value * (in_bytes + out_bytes) / 1e9,
-        "parity": "golden inputs reproduced the reference digests (tests/golden) before timing",
+        "parity": f"{checks} golden digests of the unmodified reference reproduced on every rank before timing, "
+                  f"incl. shard starts at non-zero frame offsets (tests/golden)",
     }
+    if strong:
+        line["total_frames"] = args.total_frames
+        line["shard"] = {"first": my_first, "count": my_count, "of_rank": rank}
 
     if cpu_baseline is not None:
         line["cpu_baseline"] = cpu_baseline
@@ -473,7 +552,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
-    ap.add_argument("--frames-per-step", type=int, default=0)
+    ap.add_argument("--frames-per-step", type=int, default=0, help="frames of the resident pool = frames per C-ABI call (default: 6.4 GB of input)")
+    ap.add_argument("--passes", type=int, default=0, help="C-ABI calls per step (default: ~400 GB of traffic per step)")
+    ap.add_argument("--total-frames", type=int, default=0, help="strong scaling: a step is this whole job, sharded over the ranks")
     ap.add_argument("--e2e-frames", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dst-offset", type=int, default=0, help="diagnostic: extra bytes (multiple of 256) in front of the output pool")

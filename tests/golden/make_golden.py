@@ -11,7 +11,11 @@ depth / chroma-format / gain variants it records
     gain, vfgs_main.c:208-230,561-593), so the firmware layer can be re-run elsewhere,
   * the hardware state the reference firmware programs from it (vfgs_hw.c:49-63), trimmed to the
     pattern slots in use,
-  * SHA-256 digests of the reference's output for seeded synthetic frames (see CASE_INPUTS).
+  * SHA-256 digests of the reference's output for seeded synthetic frames (see CASE_INPUTS),
+  * "shards": the reference run CONTINUOUSLY over SHARD_GROUPS groups of the first CASE_INPUTS entry (the same
+    frames fed again and again while the LFSR registers run on, vfgs_hw.c:288-312), one digest and the registers
+    per group: what a rank that starts at frame offset g * frames must reproduce after a jump-ahead
+    (bench.py's per-rank parity gate, tests/test_gpu_parity.py::test_frame_offsets_match_reference_digests).
 
 The GPU box has neither /root/reference nor cfg files; tests there read only this fixture.
 """
@@ -35,6 +39,7 @@ SEED = 12345
 # (width, height, frames, input seed): one block-aligned case whose height is not a multiple of 16,
 # one with ragged width and height (partial last block, odd chroma tail)
 CASE_INPUTS = [(256, 152, 3, 11), (200, 130, 2, 12)]
+SHARD_GROUPS = 8
 
 
 def variants(name: str):
@@ -90,8 +95,18 @@ def main() -> None:
                     ref.set_raw_rnd(int(st["lfsr"][2]))
                     out = ref.add_grain_frames(frames, n, w, h, fmt, od)
                     outs[f"{w}x{h}x{n}|s{iseed}|o{od}"] = {"sha256": sha(out), "lfsr_after": [int(v) for v in ref.state()["lfsr"]]}
+            shards = {}
+            (w, h, n, iseed) = CASE_INPUTS[0]
+            frames = synth_frames(n, w, h, fmt, depth, seed=iseed)
+            for od in ((0, 8) if depth == 10 else (0,)):
+                ref.set_raw_rnd(int(st["lfsr"][2]))
+                groups = []
+                for g in range(SHARD_GROUPS):  # the registers carry over from group to group
+                    out = ref.add_grain_frames(frames, n, w, h, fmt, od)
+                    groups.append({"sha256": sha(out), "lfsr_after": [int(v) for v in ref.state()["lfsr"]]})
+                shards[f"{w}x{h}x{n}|s{iseed}|o{od}"] = groups
             index[case] = {"load_rc": 0, "afgs1": bool(is_afgs1), "depth": depth, "fmt": fmt, "gain": gain,
-                           "nslot": nslot, "outputs": outs}
+                           "nslot": nslot, "outputs": outs, "shards": shards}
             print(case, "ok", nslot)
 
     # LFSR / offset known answers straight from the reference's static functions (vfgs_hw.c:74-138)

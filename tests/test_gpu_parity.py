@@ -179,6 +179,25 @@ def test_split_calls_and_skip_frames_equal_one_call(hw):
     assert hw.get_lfsr() == regs_whole
 
 
+@pytest.mark.parametrize("case", CASES)
+def test_frame_offsets_match_reference_digests(hw, case):
+    """Shard starts on the device: jump to frame offset g * n (vfgs_b200_skip_frames) and reproduce the digest the
+    reference recorded for that group of its continuous run (tests/golden "shards")."""
+    meta = G.cases[case]
+    epoch = [int(v) for v in G.state(case)["lfsr"]]
+    for key, groups in meta["shards"].items():
+        w, h, n, iseed, od = parse_output_key(key)
+        frames = synth_frames(n, w, h, meta["fmt"], meta["depth"], seed=iseed)
+        for g, want in enumerate(groups):
+            if g not in (0, 1, 5, 7):
+                continue
+            hw.reset(); program_case(hw, G, case)
+            hw.set_lfsr(epoch); hw.skip_frames(g * n, w, h)
+            got = run_device(hw, frames, n, w, h, od, meta["depth"])
+            assert sha(got) == want["sha256"], (case, key, g)
+            assert hw.get_lfsr() == want["lfsr_after"], (case, key, g)
+
+
 def test_padded_strides_and_unaligned_base(hw):
     """Explicit planes with yuv_alloc-style 64-sample strides (yuv.c:65,74) and a base pointer that
     defeats the 128-bit path: same samples as the packed layout."""

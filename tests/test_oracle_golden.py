@@ -21,6 +21,24 @@ def test_oracle_matches_reference_digests(case):
         assert o.get_lfsr() == want["lfsr_after"], (case, key)
 
 
+@pytest.mark.parametrize("case", G.runnable())
+def test_oracle_frame_offsets_match_reference_digests(case):
+    """The reference ran the same frames again and again while its registers carried on (make_golden.py
+    "shards"); the oracle reaches every group by jump-ahead (skip_frames) without processing the groups before."""
+    meta = G.cases[case]
+    epoch = [int(v) for v in G.state(case)["lfsr"]]
+    for key, groups in meta["shards"].items():
+        w, h, n, iseed, od = parse_output_key(key)
+        frames = synth_frames(n, w, h, meta["fmt"], meta["depth"], seed=iseed)
+        for g, want in enumerate(groups):
+            o = Oracle()
+            program_case(o, G, case)
+            o.set_lfsr(epoch)
+            o.skip_frames(g * n, w, h)
+            assert sha(o.add_grain_frames(frames, n, w, h, od)) == want["sha256"], (case, key, g)
+            assert o.get_lfsr() == want["lfsr_after"], (case, key, g)
+
+
 @pytest.mark.parametrize("case", [c for c in G.runnable() if "|d10|420|g100" in c][:8])
 def test_oracle_line_walk_equals_closed_form(case):
     """vfgs_add_grain_line driven like vfgs_main.c:664-682 == the jump-ahead frame form."""

@@ -30,11 +30,24 @@ void run_fast(const FgsParams& p, const uint8_t* lut)
 		for (int lane = 0; lane < 32; lane++) process_task_fast<IN16, OUT8>(p, smem_addr(lut), (uint32_t)task, lane);
 }
 
-template <bool IN16, bool OUT8>
+// the gather task code exchanges grain values between lanes (warp shuffle on the device): every task runs twice,
+// first recording what each lane sends, then replaying with the neighbours' values (fgs_gather.h, EmuWarp)
+template <bool IN16, bool OUT8, bool FOLD>
 void run_gather(const FgsParams& p, const uint8_t* luts, const uint8_t* img)
 {
 	for (long long task = 0; task < p.total_tasks; task++)
-		for (int lane = 0; lane < 32; lane++) process_task_gather<IN16, OUT8>(p, smem_addr(luts), smem_addr(img), (uint32_t)task, lane);
+		for (int pass = 0; pass < 2; pass++) {
+			emu_warp().record = pass == 0;
+			for (int lane = 0; lane < 32; lane++)
+				process_task_gather<IN16, OUT8, FOLD>(p, smem_addr(luts), smem_addr(img), (uint32_t)task, lane);
+		}
+}
+template <bool FOLD>
+void run_gather_any(const FgsParams& g, size_t isz, size_t osz, const uint8_t* gl, const uint8_t* gi)
+{
+	if (isz == 1) run_gather<false, false, FOLD>(g, gl, gi);
+	else if (osz == 1) run_gather<true, true, FOLD>(g, gl, gi);
+	else run_gather<true, false, FOLD>(g, gl, gi);
 }
 } // namespace
 
@@ -42,7 +55,7 @@ extern "C" int emu_state_size(void) { return (int)sizeof(StateDump); }
 
 // Packed planar frames, whole frames, like vfgs_b200_add_grain_frames_device.
 // mode: 0 automatic kernel choice, 1 general task code everywhere, 2 gather task code wherever it can
-// run (plan_launches). Returns a bit mask: 1 = fast, 2 = general, 4 = gather task code ran.
+// run (plan_launches). Returns a bit mask: 1 = fast, 2 = general, 4 = gather task code ran, 8 = with sign-folded slot copies.
 extern "C" int emu_add_grain_frames(const void* state, const void* in, void* out, int nframes, int width,
                                     int height, int out_depth, int first_frame_index, int mode)
 {
@@ -71,7 +84,7 @@ extern "C" int emu_add_grain_frames(const void* state, const void* in, void* out
 	// "shared memory" of the two kernels (the fast kernel's LUT on a 32 KB boundary, like on the device)
 	std::vector<uint32_t> tab_store((blob.size() + 64) / 4);
 	uint8_t* tab = (uint8_t*)tab_store.data();
-	memcpy(tab, blob.data(), blob.size());
+	memcpy(tab, blob.data(), (size_t)bi.bytes); // the general kernel copies the image without the negated slot copies
 	// the fast kernel's shared window: LUTs on a 32 KB boundary, dynamic shared memory starting kEmuPad bytes
 	// in front of it (1 KB reserved by the driver + 128 B of static variables on the device)
 	constexpr int kEmuPad = kLutAlign - 1152;
@@ -147,14 +160,13 @@ extern "C" int emu_add_grain_frames(const void* state, const void* in, void* out
 				lut[i] = (e & 0xffu) | (((e >> 8) * slot_bytes) << 8);
 			}
 		}
-		if (isz == 1) run_gather<false, false>(g, gl, gi);
-		else if (osz == 1) run_gather<true, true>(g, gl, gi);
-		else run_gather<true, false>(g, gl, gi);
+		if (lp.gather_fold) run_gather_any<true>(g, isz, osz, gl, gi);
+		else run_gather_any<false>(g, isz, osz, gl, gi);
 	}
 	if (lp.any_general)
 		for (long long task = 0; task < lp.general.total_tasks; task++)
 			for (int lane = 0; lane < 32; lane++) process_task(lp.general, tab, (uint32_t)task, lane);
-	return (lp.any_fast ? 1 : 0) | (lp.any_general ? 2 : 0) | (lp.any_gather ? 4 : 0);
+	return (lp.any_fast ? 1 : 0) | (lp.any_general ? 2 : 0) | (lp.any_gather ? 4 : 0) | (lp.any_gather && lp.gather_fold ? 8 : 0);
 }
 
 // Launch planning of a whole-frame call, without running anything (host logic only): which kernel serves each

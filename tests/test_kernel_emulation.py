@@ -23,7 +23,8 @@ def emu():
 
 def run_emu(emu, o: Oracle, frames, n, w, h, od, first=0, mode=0):
     """mode: 0 automatic, 1 general task code only, 2 gather task code wherever possible.
-    Returns (output, mask): mask bit 0 = fast, bit 1 = general, bit 2 = gather task code ran."""
+    Returns (output, mask): mask bit 0 = fast, bit 1 = general, bit 2 = gather task code ran, bit 3 = the gather
+    code read sign-folded slot copies."""
     st = RefState()
     o.L.oracle_get_state(o.h, C.byref(st))
     depth = 8 + st.bs
@@ -45,6 +46,7 @@ def test_emulated_kernel_equals_oracle(emu, case):
                 assert np.array_equal(got, want), (case, w, h, od, mode, first_mismatch(got, want, w, h, meta["fmt"], n))
                 assert mode != 1 or mask == 2
                 assert mode != 2 or (mask & 1) == 0
+
 
 
 def test_emulated_kernel_frame_offset(emu):
@@ -71,8 +73,8 @@ def test_fast_path_is_taken_where_expected(emu):
     assert mask_of("fgs_afgs1_test1.cfg|d10|420|g100", 512, 64) == 1
     assert mask_of("fgs_sei_ff_test4.cfg|d10|444|g150", 512, 64) == 1
     assert mask_of("fgs_sei_ff_test1.cfg|d8|420|g100", 512, 64) == 1
-    assert mask_of("fgs_sei.cfg|d10|420|g100", 512, 64) == 5          # luma: gather, chroma: fast
-    assert mask_of("fgs_sei_ff_test5.cfg|d10|420|g100", 512, 64) == 5  # chroma: gather
+    assert mask_of("fgs_sei.cfg|d10|420|g100", 512, 64) == 13          # luma: gather (sign-folded slot copies), chroma: fast
+    assert mask_of("fgs_sei_ff_test5.cfg|d10|420|g100", 512, 64) == 13  # chroma: gather
     assert mask_of("fgs_afgs1_test1.cfg|d10|420|g100", 200, 64) == 3   # luma rows qualify, chroma width 100 does not
     assert mask_of("fgs_afgs1_test1.cfg|d10|420|g100", 204, 64) == 2
 
@@ -92,7 +94,7 @@ def test_fast_path_garbage_samples_and_minus_128(emu):
     o = Oracle(); program_case(o, G, case); o.vfgs_set_luma_pattern(0, np.ascontiguousarray(P))
     frames = synth_frames(n, w, h, "420", 10, seed=2)
     got, mask = run_emu(emu, o, frames, n, w, h, 0)
-    assert mask == 5 and np.array_equal(got, o.add_grain_frames(frames, n, w, h, 0))
+    assert mask == 5 and np.array_equal(got, o.add_grain_frames(frames, n, w, h, 0))  # gather code, sign by multiplication
 
 
 @pytest.mark.parametrize("w,h,n", [(144, 1, 2), (144, 15, 3), (136, 16, 2), (160, 17, 2), (130, 31, 1), (16384, 18, 1), (8200, 20, 1)])

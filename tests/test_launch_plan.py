@@ -44,7 +44,10 @@ def test_headline_config_layout(emu):
 def test_kernel_choice(emu):
     o = Oracle(); program_case(o, G, "fgs_sei.cfg|d10|420|g100")           # 8 luma patterns
     assert plan(emu, o, 512, 64)["kind"] == [GATHER, FAST, FAST]
-    assert plan(emu, o, 512, 64, in_place=1)["kind"] == [GENERAL, FAST, FAST]  # the shim routes this through a scratch buffer instead
+    assert plan(emu, o, 512, 64, in_place=1)["kind"] == [GATHER, FAST, FAST]   # 16-sample-block gather lanes read only their own samples
+    o5 = Oracle(); program_case(o5, G, "fgs_sei_ff_test5.cfg|d10|420|g100")  # sample-adaptive 4:2:0 chroma: 8-sample blocks
+    assert plan(emu, o5, 512, 64)["kind"] == [FAST, GATHER, GATHER]
+    assert plan(emu, o5, 512, 64, in_place=1)["kind"] == [FAST, GENERAL, GENERAL]  # halo lanes would read overwritten input: the shim takes the scratch route
     assert plan(emu, o, 512, 64, mode=1)["kind"] == [GENERAL] * 3
     assert plan(emu, o, 204, 64)["kind"] == [GENERAL] * 3                  # 204 % 8 != 0, chroma rows unaligned
     o = Oracle(); program_case(o, G, "fgs_afgs1_test1.cfg|d10|420|g100")

@@ -190,8 +190,8 @@ int upload_blob()
 		return set_err(VFGS_B200_ERR_STATE, "table image of %d bytes exceeds shared memory", g_bi.bytes);
 	// frames still in flight read the old image: drain before overwriting (config changes are rare)
 	CUDA_TRY(cudaDeviceSynchronize());
-	if (int rc = grow(c.d_blob, c.blob_cap, (size_t)g_bi.bytes)) return rc;
-	CUDA_TRY(cudaMemcpy(c.d_blob, g_blob.data(), (size_t)g_bi.bytes, cudaMemcpyHostToDevice));
+	if (int rc = grow(c.d_blob, c.blob_cap, (size_t)g_bi.gbytes)) return rc;
+	CUDA_TRY(cudaMemcpy(c.d_blob, g_blob.data(), (size_t)g_bi.gbytes, cudaMemcpyHostToDevice));
 	if (g_bi.bytes > c.smem_attr) {
 		CUDA_TRY(cudaFuncSetAttribute(fgs_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_bi.bytes));
 		c.smem_attr = g_bi.bytes;
@@ -247,7 +247,14 @@ void fill_common(FgsParams& p, const Geometry& g)
 typedef void (*GrainKernel)(const FgsParams);
 enum KernelKind { kGeneral = 0, kFast = 1, kGather = 2 };
 
-int launch_apply(const FgsParams& p, cudaStream_t stream, KernelKind kind = kGeneral, int gather_smem = 0)
+template <bool FOLD>
+GrainKernel gather_kernel(const FgsParams& p)
+{
+	return p.in_bytes == 1 ? fgs_apply_gather_kernel<false, false, FOLD>
+	     : p.out_bytes == 1 ? fgs_apply_gather_kernel<true, true, FOLD> : fgs_apply_gather_kernel<true, false, FOLD>;
+}
+
+int launch_apply(const FgsParams& p, cudaStream_t stream, KernelKind kind = kGeneral, int gather_smem = 0, bool gather_fold = false)
 {
 	Context& c = g_ctx;
 	if (p.total_tasks <= 0) return VFGS_B200_OK;
@@ -265,13 +272,15 @@ int launch_apply(const FgsParams& p, cudaStream_t stream, KernelKind kind = kGen
 			c.fast_smem_attr = smem;
 		}
 	} else if (kind == kGather) {
-		kern = p.in_bytes == 1 ? fgs_apply_gather_kernel<false, false>
-		     : p.out_bytes == 1 ? fgs_apply_gather_kernel<true, true> : fgs_apply_gather_kernel<true, false>;
+		kern = gather_fold ? gather_kernel<true>(p) : gather_kernel<false>(p);
 		threads = kGatherThreads; smem = gather_smem;
 		if (smem > c.gather_smem_attr) {
-			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_gather_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_gather_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_gather_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_gather_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_gather_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_gather_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_gather_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_gather_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_gather_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 			c.gather_smem_attr = smem;
 		}
 	}
@@ -329,12 +338,10 @@ void advance_registers(const Geometry& g, uint64_t nframes)
 	h.rnd_up = jt.jump(h.line_rnd_up, (uint64_t)g.nb);
 }
 
-// Streams + grain kernels for `n` frames whose epoch-relative index starts at frame0.
-int run_frames_device(const vfgs_b200_planes& in, const vfgs_b200_planes& out, int n, const Geometry& g,
-                      uint32_t epoch, uint64_t frame0, uint32_t* d_streams, cudaStream_t stream,
-                      cudaStream_t table_stream = nullptr, cudaEvent_t table_ready = nullptr)
+// Launch parameters and kernel assignment of a whole-frame call.
+void plan_frames(const vfgs_b200_planes& in, const vfgs_b200_planes& out, int n, const Geometry& g, bool in_place,
+                 uint32_t* d_streams, FgsParams& p, LaunchPlan& lp, uint16_t*& d_woffs)
 {
-	FgsParams p;
 	fill_common(p, g);
 	p.nframes = n;
 	p.y_begin = 0; p.y_end = g.height;
@@ -350,13 +357,34 @@ int run_frames_device(const vfgs_b200_planes& in, const vfgs_b200_planes& out, i
 		p.comp[c].lines = c ? g.ch : g.height;
 	}
 	// one allocation holds both per-block tables: uint32 registers, then 4 x uint16 window offsets
-	uint16_t* d_woffs = (uint16_t*)(d_streams + (((size_t)n * g.R * g.spitch + 3) & ~(size_t)3)); // 16-byte aligned
+	d_woffs = (uint16_t*)(d_streams + (((size_t)n * g.R * g.spitch + 3) & ~(size_t)3)); // 16-byte aligned
 	p.states = d_streams; p.woffs = d_woffs; p.stream_rows = g.R; p.stream_row0 = 0;
 	finish_tasks(p);
 	// every component goes to the cheapest kernel that can serve it (plan_launches)
-	g_ctx.last_launch[4] = 0;
+	plan_launches(p, g_bi, g_kernel_mode, in_place, g_ctx.max_smem_optin - 1024, g_ctx.fast_pad, lp);
+}
+
+// In place, a kernel must not read what another warp may already have overwritten. The fast kernel and the gather
+// kernel's 16-sample-block lanes read nothing but their own samples; the general kernel (and the gather kernel's
+// 8-sample-block halo lanes, which plan_launches therefore never uses in place) read a neighbouring block's INPUT
+// sample when the pattern slot depends on the sample: those calls go through a scratch output buffer.
+bool in_place_needs_scratch(const LaunchPlan& lp)
+{
+	for (int c = 0; c < 3; c++)
+		if (lp.kind[c] == 2 && g_bi.uniform_pi[c] < 0) return true;
+	return false;
+}
+
+// Streams + grain kernels for `n` frames whose epoch-relative index starts at frame0.
+int run_frames_device(const vfgs_b200_planes& in, const vfgs_b200_planes& out, int n, const Geometry& g, bool in_place,
+                      uint32_t epoch, uint64_t frame0, uint32_t* d_streams, cudaStream_t stream,
+                      cudaStream_t table_stream = nullptr, cudaEvent_t table_ready = nullptr)
+{
+	FgsParams p;
 	LaunchPlan lp;
-	plan_launches(p, g_bi, g_kernel_mode, in.y == out.y, g_ctx.max_smem_optin - 1024, g_ctx.fast_pad, lp);
+	uint16_t* d_woffs = nullptr;
+	plan_frames(in, out, n, g, in_place, d_streams, p, lp, d_woffs);
+	g_ctx.last_launch[4] = 0;
 	// the register table feeds the general kernel, the window-offset table the fast and gather kernels
 	if (int rc = launch_streams(epoch, lp.any_general ? d_streams : nullptr, (lp.any_fast || lp.any_gather) ? d_woffs : nullptr,
 	                            make_woff_params(p, lp.kind), n, g, frame0, table_stream ? table_stream : stream)) return rc;
@@ -367,10 +395,35 @@ int run_frames_device(const vfgs_b200_planes& in, const vfgs_b200_planes& out, i
 	if (lp.any_fast)
 		if (int rc = launch_apply(lp.fast, stream, kFast)) return rc;
 	if (lp.any_gather)
-		if (int rc = launch_apply(lp.gather, stream, kGather, lp.gather_smem)) return rc;
+		if (int rc = launch_apply(lp.gather, stream, kGather, lp.gather_smem, lp.gather_fold)) return rc;
 	if (lp.any_general)
 		if (int rc = launch_apply(lp.general, stream, kGeneral)) return rc;
 	return VFGS_B200_OK;
+}
+
+// How the output planes lie relative to the input planes: 0 disjoint, 1 in place (every overlapping plane pair is
+// the same plane with the same strides and sample size), -1 anything else (partial overlap: not supported).
+int aliasing(const vfgs_b200_planes& in, const vfgs_b200_planes& out, int n, const Geometry& g)
+{
+	const uint8_t* ip[3] = {(const uint8_t*)in.y, (const uint8_t*)in.u, (const uint8_t*)in.v};
+	const uint8_t* op[3] = {(const uint8_t*)out.y, (const uint8_t*)out.u, (const uint8_t*)out.v};
+	auto extent = [&](const vfgs_b200_planes& pl, int c, size_t sample) {
+		const int64_t lines = c ? g.ch : g.height, width = c ? g.cw : g.width;
+		if (lines < 1 || width < 1) return (int64_t)0;
+		return (int64_t)(n - 1) * pl.frame_stride + (lines - 1) * (c ? pl.stride_c : pl.stride_y) + width * (int64_t)sample;
+	};
+	int result = 0;
+	for (int i = 0; i < 3; i++)
+		for (int j = 0; j < 3; j++) {
+			const int64_t ei = extent(in, i, g.in_sample), ej = extent(out, j, g.out_sample);
+			if (ei <= 0 || ej <= 0) continue;
+			if (ip[i] + ei <= op[j] || op[j] + ej <= ip[i]) continue; // disjoint byte ranges
+			const bool same = i == j && ip[i] == op[j] && g.in_sample == g.out_sample && in.frame_stride == out.frame_stride &&
+			                  (i ? in.stride_c == out.stride_c : in.stride_y == out.stride_y);
+			if (!same) return -1;
+			result = 1;
+		}
+	return result;
 }
 
 void packed_planes(vfgs_b200_planes& pl, const void* base, const Geometry& g, size_t sample, size_t frame_bytes)
@@ -502,7 +555,10 @@ void vfgs_add_grain_line(void* Y, void* U, void* V, int y, int width)
 	auto chk = [](cudaError_t e, const char* what) {
 		if (e != cudaSuccess) { snprintf(g_err, sizeof(g_err), "%s -> %s", what, cudaGetErrorString(e)); fatal("vfgs_add_grain_line"); }
 	};
-	if (grow(c.d_line, c.line_cap, lpad + 2 * cpad)) fatal("vfgs_add_grain_line");
+	// the line is staged OUT OF PLACE (input region, then output region): with sample-adaptive pattern selection the
+	// general kernel reads the neighbouring block's input sample, which another warp may already have overwritten
+	const size_t region = lpad + 2 * cpad;
+	if (grow(c.d_line, c.line_cap, 2 * region)) fatal("vfgs_add_grain_line");
 	if (grow(c.d_streams, c.streams_cap, rows.size() * sizeof(uint32_t))) fatal("vfgs_add_grain_line");
 	cudaStream_t st = c.s_k;
 	if (c.used_stream && c.last_stream != st) chk(cudaStreamSynchronize(c.last_stream), "sync");
@@ -520,7 +576,7 @@ void vfgs_add_grain_line(void* Y, void* U, void* V, int y, int width)
 	p.row_begin = y >> 4; p.rows = 1;
 	uint8_t* base[3] = {c.d_line, c.d_line + lpad, c.d_line + lpad + cpad};
 	for (int k = 0; k < 3; k++) {
-		p.comp[k].in = base[k]; p.comp[k].out = base[k];
+		p.comp[k].in = base[k]; p.comp[k].out = base[k] + region;
 		p.comp[k].in_row_bytes = p.comp[k].out_row_bytes = 0; // every line index maps to the staged line
 		p.comp[k].width = k ? g.cw : width;
 		p.comp[k].lines = (k && !chroma) ? 0 : 0x7fffffff;
@@ -528,10 +584,10 @@ void vfgs_add_grain_line(void* Y, void* U, void* V, int y, int width)
 	p.states = c.d_streams; p.stream_rows = 2; p.stream_row0 = (y >> 4) - 1;
 	finish_tasks(p);
 	if (launch_apply(p, st)) fatal("vfgs_add_grain_line");
-	chk(cudaMemcpyAsync(Y, c.d_line, lbytes, cudaMemcpyDeviceToHost, st), "Y D2H");
+	chk(cudaMemcpyAsync(Y, c.d_line + region, lbytes, cudaMemcpyDeviceToHost, st), "Y D2H");
 	if (chroma) {
-		chk(cudaMemcpyAsync(U, c.d_line + lpad, cbytes, cudaMemcpyDeviceToHost, st), "U D2H");
-		chk(cudaMemcpyAsync(V, c.d_line + lpad + cpad, cbytes, cudaMemcpyDeviceToHost, st), "V D2H");
+		chk(cudaMemcpyAsync(U, c.d_line + region + lpad, cbytes, cudaMemcpyDeviceToHost, st), "U D2H");
+		chk(cudaMemcpyAsync(V, c.d_line + region + lpad + cpad, cbytes, cudaMemcpyDeviceToHost, st), "V D2H");
 	}
 	chk(cudaStreamSynchronize(st), "line sync");
 
@@ -567,16 +623,26 @@ int vfgs_b200_add_grain_planes_device(const vfgs_b200_planes* in, const vfgs_b20
 	if (int rc = make_geometry(g, width, height, out_depth)) return rc;
 	if (int rc = prepare(-1)) return rc;
 	if (nframes == 0) return VFGS_B200_OK;
-	if (in->y == out->y && g.in_depth != g.out_depth) return set_err(VFGS_B200_ERR_ARG, "in-place needs equal depths");
+	const int alias = aliasing(*in, *out, nframes, g);
+	if (alias < 0)
+		return set_err(VFGS_B200_ERR_ARG, g.in_depth != g.out_depth ? "in-place needs equal depths"
+		               : "input and output planes overlap without being identical (same planes, strides and depth)");
+	const bool in_place = alias == 1;
 	Context& c = g_ctx;
 	cudaStream_t st = (cudaStream_t)stream;
 	if (c.used_stream && c.last_stream != st) CUDA_TRY(cudaStreamSynchronize(c.last_stream)); // d_streams is shared
 	c.last_stream = st; c.used_stream = true;
-	if (in->y == out->y && !all_uniform()) {
-		// In place with sample-adaptive pattern selection: a block's edge filter reads the neighbouring block's
-		// INPUT sample, which another warp may already have overwritten. The frames go through a scratch output
-		// buffer in sub-batches and are copied back (two extra passes over the data; the reference's own
-		// in-place order, block after block along a line, has no such hazard).
+	bool scratch = false;
+	if (in_place) { // cheap host-side planning pass: which kernels would serve the components
+		FgsParams pp; LaunchPlan lpp; uint16_t* w = nullptr;
+		plan_frames(*in, *out, nframes, g, true, nullptr, pp, lpp, w);
+		scratch = in_place_needs_scratch(lpp);
+	}
+	if (scratch) {
+		// In place with sample-adaptive pattern selection on a kernel that reads the neighbouring block's INPUT
+		// sample (see in_place_needs_scratch), which another warp may already have overwritten. The frames go
+		// through a scratch output buffer in sub-batches and are copied back (two extra passes over the data; the
+		// reference's own in-place order, block after block along a line, has no such hazard).
 		const size_t fb = g.out_frame_bytes;
 		int per = (int)((256u << 20) / fb);
 		if (per < 1) per = 1;
@@ -592,7 +658,7 @@ int vfgs_b200_add_grain_planes_device(const vfgs_b200_planes* in, const vfgs_b20
 			pi.u = (uint8_t*)in->u + (size_t)f0 * in->frame_stride;
 			pi.v = (uint8_t*)in->v + (size_t)f0 * in->frame_stride;
 			packed_planes(po, c.d_scratch, g, g.out_sample, g.out_frame_bytes);
-			if (int rc = run_frames_device(pi, po, n, g, epoch, (uint64_t)f0, c.d_streams, st)) return rc;
+			if (int rc = run_frames_device(pi, po, n, g, false, epoch, (uint64_t)f0, c.d_streams, st)) return rc;
 			for (int f = 0; f < n; f++) { // rows of the caller's planes may be padded: 2-D copies, plane by plane
 				const uint8_t* s = c.d_scratch + (size_t)f * fb;
 				uint8_t* dy = (uint8_t*)out->y + (size_t)(f0 + f) * out->frame_stride;
@@ -610,7 +676,7 @@ int vfgs_b200_add_grain_planes_device(const vfgs_b200_planes* in, const vfgs_b20
 	const int t = (int)(c.tab_next++ & 1u);
 	if (int rc = grow(c.d_tab[t], c.tab_cap[t], (size_t)nframes * g.R * g.spitch * kBlockTableBytes + 16)) return rc;
 	if (c.tab_used[t]) CUDA_TRY(cudaStreamWaitEvent(c.s_tab, c.tab_free[t], 0)); // the grain kernels of two calls ago read this buffer
-	if (int rc = run_frames_device(*in, *out, nframes, g, hw().line_rnd, 0, c.d_tab[t], st, c.s_tab, c.tab_ready[t])) return rc;
+	if (int rc = run_frames_device(*in, *out, nframes, g, in_place, hw().line_rnd, 0, c.d_tab[t], st, c.s_tab, c.tab_ready[t])) return rc;
 	CUDA_TRY(cudaEventRecord(c.tab_free[t], st));
 	c.tab_used[t] = true;
 	advance_registers(g, (uint64_t)nframes);
@@ -669,7 +735,7 @@ int vfgs_b200_add_grain_frames_host(const void* in, void* out, int nframes, int 
 		vfgs_b200_planes pi, po;
 		packed_planes(pi, s.d_in, g, g.in_sample, g.in_frame_bytes);
 		packed_planes(po, s.d_out, g, g.out_sample, g.out_frame_bytes);
-		if (int rc = run_frames_device(pi, po, n, g, epoch, (uint64_t)f0, s.d_streams, c.s_k)) return rc;
+		if (int rc = run_frames_device(pi, po, n, g, false, epoch, (uint64_t)f0, s.d_streams, c.s_k)) return rc;
 		CUDA_TRY(cudaEventRecord(s.k_done, c.s_k));
 		CUDA_TRY(cudaStreamWaitEvent(c.s_d2h, s.k_done, 0));
 		CUDA_TRY(cudaMemcpyAsync(hout + (size_t)f0 * g.out_frame_bytes, s.d_out, (size_t)n * g.out_frame_bytes, cudaMemcpyDeviceToHost, c.s_d2h));

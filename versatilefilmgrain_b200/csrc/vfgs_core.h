@@ -192,10 +192,14 @@ struct FgsParams {
 	int fpat_off[3][2];     // +pattern / -pattern copies, relative to the component's image
 	int fpat_stride[3];
 	int fpat_copy[3];       // bytes between the column-shifted copies of a pattern
-	// gather path (fgs_gather.h): private LUT slot of each component (-1: none) and the pattern banks'
-	// offsets inside the general image
+	// gather path (fgs_gather.h): private LUT slot of each component (-1: none), the pattern banks' offsets inside
+	// the general image and (sign-folded launches) the distance from a bank's slots to their negated copies
 	int glut_index[3], ngather;
-	int gpat_off[2];
+	int gpat_off[2], gneg_off[2];
+	// gather kernel task numbering: a component's stripes are one flat run of 8-sample lane units, rows padded to an
+	// even number of units; a warp-task holds 32 (16-sample blocks) or 30 (8-sample blocks) consecutive units
+	int gunits_per_row[3], gtasks[3], gtasks_per_frame;
+	FastDiv div_gunits[3], div_gtasks;
 	// LFSR register per block: row (f * stream_rows + r - stream_row0) holds spitch words, word b + 1 is
 	// the register of block b of that block-row (words 0 and nb + 1 are padding for the b-1 / b+1 reads)
 	const uint32_t* states;

@@ -186,7 +186,8 @@ fgs_apply_fast_kernel(const __grid_constant__ FgsParams p)
 
 // Gather path: components with sample-adaptive pattern selection (fgs_gather.h). Shared memory: one
 // per-lane replicated LUT (32 KB, entry = scale | slot byte offset << 8) per gather component, each on a
-// 32 KB boundary, then the general table image (compact LUTs + pattern slots) brought in by one bulk copy.
+// 32 KB boundary, then the general table image (compact LUTs + pattern slots; FOLD: + the negated slots)
+// brought in by one bulk copy.
 #ifndef VFGS_GATHER_THREADS
 #define VFGS_GATHER_THREADS 896
 #define VFGS_GATHER_CTAS 1
@@ -195,7 +196,7 @@ constexpr int kGatherThreads = VFGS_GATHER_THREADS; // one CTA per SM at up to 7
                                                     // measured ahead of 2 x 384 (one table image per SM) and of 640-832 and 960-1024 threads
 constexpr int kGatherWarps = kGatherThreads / 32;
 
-template <bool IN16, bool OUT8>
+template <bool IN16, bool OUT8, bool FOLD>
 __global__ void __launch_bounds__(kGatherThreads, VFGS_GATHER_CTAS)
 fgs_apply_gather_kernel(const __grid_constant__ FgsParams p)
 {
@@ -228,7 +229,7 @@ fgs_apply_gather_kernel(const __grid_constant__ FgsParams p)
 	const smem_addr_t luts = smem_addr(lut_ptr), img = smem_addr(img_ptr);
 	const long long stride = (long long)gridDim.x * kGatherWarps;
 	for (long long task = (long long)blockIdx.x * kGatherWarps + (threadIdx.x >> 5); task < p.total_tasks; task += stride)
-		process_task_gather<IN16, OUT8>(p, luts, img, (uint32_t)task, lane);
+		process_task_gather<IN16, OUT8, FOLD>(p, luts, img, (uint32_t)task, lane);
 }
 
 } // namespace vfgs

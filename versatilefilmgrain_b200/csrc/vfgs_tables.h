@@ -46,6 +46,10 @@ struct HwState {
 struct TableInfo {
 	// general image (fgs_task.h)
 	int lut_off, pat_off[2], pat_size[2], pat_stride[2], uniform_pi[3], bytes;
+	// sign-folded gather launches: the slots in use once more, negated, behind the general image (a bank takes part
+	// when none of its slots in use holds a -128 byte); gbytes = size of the image including them
+	int nslot[2], neg_off[2], gbytes;
+	bool neg_ok[2];
 	// fast image (fgs_fast.h): usable for a component when its pattern LUT selects one slot and that
 	// slot has no -128 byte (so that -pattern fits int8)
 	bool fast_ok[3];
@@ -79,7 +83,19 @@ inline void build_tables(const HwState& h, TableInfo& g_bi, std::vector<uint8_t>
 	g_bi.pat_off[1] = g_bi.pat_off[0] + nslot[0] * g_bi.pat_size[0];
 	g_bi.pat_size[1] = crows * cpitch; g_bi.pat_stride[1] = cpitch;
 	g_bi.bytes = (g_bi.pat_off[1] + nslot[1] * g_bi.pat_size[1] + 16 + 15) & ~15; // +16: fetch8 may touch one word past an octet
-	g_blob.assign((size_t)g_bi.bytes, 0);
+	g_bi.gbytes = g_bi.bytes;
+	for (int b = 0; b < 2; b++) { // negated copies of the banks' slots (gather kernel, sign folding)
+		g_bi.nslot[b] = nslot[b];
+		g_bi.neg_ok[b] = true;
+		for (int s = 0; s < nslot[b] && g_bi.neg_ok[b]; s++)
+			for (int r = 0; r < 64 && g_bi.neg_ok[b]; r++)
+				for (int x = 0; x < 64; x++)
+					if (h.pattern[b][s][r][x] == -128) { g_bi.neg_ok[b] = false; break; }
+		g_bi.neg_off[b] = g_bi.gbytes - g_bi.pat_off[b]; // relative to the bank's plain slots
+		g_bi.gbytes += nslot[b] * g_bi.pat_size[b];
+	}
+	g_bi.gbytes = (g_bi.gbytes + 15) & ~15;
+	g_blob.assign((size_t)g_bi.gbytes, 0);
 	uint16_t* lut = (uint16_t*)g_blob.data();
 	for (int c = 0; c < 3; c++)
 		for (int i = 0; i < 256; i++) lut[c * 256 + i] = (uint16_t)(h.slut[c][i] | ((h.plut[c][i] >> 4) << 8));
@@ -89,6 +105,14 @@ inline void build_tables(const HwState& h, TableInfo& g_bi, std::vector<uint8_t>
 	for (int s = 0; s < nslot[1]; s++)
 		for (int r = 0; r < crows; r++)
 			memcpy(&g_blob[g_bi.pat_off[1] + s * g_bi.pat_size[1] + r * cpitch], h.pattern[1][s][r], (size_t)ccols);
+	for (int b = 0; b < 2; b++) {
+		if (!g_bi.neg_ok[b]) continue;
+		const int rows = b ? crows : 64, cols = b ? ccols : 64, pitch = g_bi.pat_stride[b];
+		for (int s = 0; s < nslot[b]; s++)
+			for (int r = 0; r < rows; r++)
+				for (int x = 0; x < cols; x++)
+					g_blob[g_bi.pat_off[b] + g_bi.neg_off[b] + s * g_bi.pat_size[b] + r * pitch + x] = (uint8_t)(int8_t)-h.pattern[b][s][r][x];
+	}
 
 	// fast-path image: compact scale LUT, then per component the single slot as +pattern and -pattern, each in
 	// fast_copies() column-shifted copies (copy k holds the pattern moved left by k * 8 / copies bytes), so that
@@ -220,6 +244,7 @@ struct LaunchPlan {
 	bool any_fast, any_gather, any_general;
 	int kind[3];     // per component: 0 fast, 1 gather, 2 general kernel
 	int gather_smem; // dynamic shared memory of the gather launch
+	bool gather_fold; // the gather launch reads sign-folded slot copies (fgs_gather.h, FOLD)
 };
 
 inline void plan_launches(const FgsParams& p, const TableInfo& bi, int mode, bool in_place, int smem_limit, int fast_pad, LaunchPlan& lp)
@@ -232,8 +257,11 @@ inline void plan_launches(const FgsParams& p, const TableInfo& bi, int mode, boo
 		const bool aligned = p.comp[c].vec && (p.comp[c].width % kSamplesPerLane) == 0;
 		kind[c] = 2;
 		if (aligned && mode != 1) {
+			// in place: the gather kernel's 8-sample-block lanes recompute their warp neighbours from INPUT samples
+			// another warp may already have overwritten; 16-sample-block lanes read nothing but their own samples
+			const bool block8 = c && p.subx > 1;
 			if (bi.fast_ok[c] && mode != 2) kind[c] = 0;
-			else if (!in_place) kind[c] = 1;
+			else if (!in_place || !block8) kind[c] = 1;
 		}
 		if (kind[c] == 1) ngather++;
 	}
@@ -246,10 +274,17 @@ inline void plan_launches(const FgsParams& p, const TableInfo& bi, int mode, boo
 			place_fast_images(lp.fast, bi, fast_pad, served);
 		}
 	}
-	lp.gather_smem = kLutAlign + ngather * kLutBytes + bi.bytes;
+	// sign folding needs the negated copies of every bank a gather component reads, and room for them
+	lp.gather_fold = ngather > 0;
+	for (int c = 0; c < 3; c++) if (kind[c] == 1 && !bi.neg_ok[c ? 1 : 0]) lp.gather_fold = false;
+	if (lp.gather_fold && kLutAlign + ngather * kLutBytes + bi.gbytes > smem_limit) lp.gather_fold = false;
+#ifdef VFGS_GATHER_NO_FOLD
+	lp.gather_fold = false; // build-time knob for experiments
+#endif
+	lp.gather_smem = kLutAlign + ngather * kLutBytes + (lp.gather_fold ? bi.gbytes : bi.bytes);
 	if (ngather && lp.gather_smem > smem_limit) { // tables do not fit: those components take the general kernel
 		for (int c = 0; c < 3; c++) if (kind[c] == 1) kind[c] = 2;
-		ngather = 0;
+		ngather = 0; lp.gather_fold = false;
 	}
 	int gi = 0;
 	for (int c = 0; c < 3; c++) {
@@ -277,12 +312,29 @@ inline void plan_launches(const FgsParams& p, const TableInfo& bi, int mode, boo
 	}
 	lp.gather.ngather = ngather;
 	lp.gather.gpat_off[0] = bi.pat_off[0]; lp.gather.gpat_off[1] = bi.pat_off[1];
+	lp.gather.gneg_off[0] = bi.neg_off[0]; lp.gather.gneg_off[1] = bi.neg_off[1];
+	lp.gather.blob_bytes = lp.gather_fold ? bi.gbytes : bi.bytes;
+	{ // the gather kernel numbers its tasks over flat runs of lane units as well (gather_task_body)
+		FgsParams& g = lp.gather;
+		g.gtasks_per_frame = 0;
+		for (int c = 0; c < 3; c++) {
+			const bool block8 = c && g.subx > 1;
+			const int upr = kind[c] == 1 ? ((g.comp[c].width + kSamplesPerLane - 1) / kSamplesPerLane + 1) & ~1 : 0;
+			const long long units = (long long)upr * g.rows;
+			g.gunits_per_row[c] = upr;
+			g.gtasks[c] = kind[c] != 1 ? 0 : block8 ? (int)((units + kGatherUnits8 - 1) / kGatherUnits8) : (int)((units + 1 + 31) / 32);
+			g.gtasks_per_frame += g.gtasks[c];
+			g.div_gunits[c] = make_fastdiv((uint32_t)(upr > 0 ? upr : 1));
+		}
+		g.div_gtasks = make_fastdiv((uint32_t)(g.gtasks_per_frame > 0 ? g.gtasks_per_frame : 1));
+	}
 	for (FgsParams* q : {&lp.fast, &lp.gather, &lp.general}) {
 		q->tasks_per_stripe = q->nseg[0] + q->nseg[1] + q->nseg[2];
 		q->total_tasks = (long long)q->nframes * q->rows * q->tasks_per_stripe;
 		q->div_tps = make_fastdiv((uint32_t)(q->tasks_per_stripe > 0 ? q->tasks_per_stripe : 1));
 	}
 	lp.fast.total_tasks = (long long)lp.fast.nframes * lp.fast.ftasks_per_frame;
+	lp.gather.total_tasks = (long long)lp.gather.nframes * lp.gather.gtasks_per_frame;
 }
 
 // What lfsr_states_kernel needs to turn a block register into a pattern-window offset (FgsParams::woffs).

@@ -32,22 +32,22 @@ void run_fast(const FgsParams& p, const uint8_t* lut)
 
 // the gather task code exchanges grain values between lanes (warp shuffle on the device): every task runs twice,
 // first recording what each lane sends, then replaying with the neighbours' values (fgs_gather.h, EmuWarp)
-template <bool IN16, bool OUT8, bool FOLD>
+template <bool IN16, bool OUT8, bool FOLD, bool SHIFT>
 void run_gather(const FgsParams& p, const uint8_t* luts, const uint8_t* img)
 {
 	for (long long task = 0; task < p.total_tasks; task++)
 		for (int pass = 0; pass < 2; pass++) {
 			emu_warp().record = pass == 0;
 			for (int lane = 0; lane < 32; lane++)
-				process_task_gather<IN16, OUT8, FOLD>(p, smem_addr(luts), smem_addr(img), (uint32_t)task, lane);
+				process_task_gather<IN16, OUT8, FOLD, SHIFT>(p, smem_addr(luts), smem_addr(img), (uint32_t)task, lane);
 		}
 }
-template <bool FOLD>
+template <bool FOLD, bool SHIFT>
 void run_gather_any(const FgsParams& g, size_t isz, size_t osz, const uint8_t* gl, const uint8_t* gi)
 {
-	if (isz == 1) run_gather<false, false, FOLD>(g, gl, gi);
-	else if (osz == 1) run_gather<true, true, FOLD>(g, gl, gi);
-	else run_gather<true, false, FOLD>(g, gl, gi);
+	if (isz == 1) run_gather<false, false, FOLD, SHIFT>(g, gl, gi);
+	else if (osz == 1) run_gather<true, true, FOLD, SHIFT>(g, gl, gi);
+	else run_gather<true, false, FOLD, SHIFT>(g, gl, gi);
 }
 } // namespace
 
@@ -55,7 +55,7 @@ extern "C" int emu_state_size(void) { return (int)sizeof(StateDump); }
 
 // Packed planar frames, whole frames, like vfgs_b200_add_grain_frames_device.
 // mode: 0 automatic kernel choice, 1 general task code everywhere, 2 gather task code wherever it can
-// run (plan_launches). Returns a bit mask: 1 = fast, 2 = general, 4 = gather task code ran, 8 = with sign-folded slot copies.
+// run (plan_launches). Returns a bit mask: 1 = fast, 2 = general, 4 = gather task code ran, 8 = with sign-folded slot copies, 16 = with the shifted unit numbering (in place).
 extern "C" int emu_add_grain_frames(const void* state, const void* in, void* out, int nframes, int width,
                                     int height, int out_depth, int first_frame_index, int mode)
 {
@@ -160,13 +160,13 @@ extern "C" int emu_add_grain_frames(const void* state, const void* in, void* out
 				lut[i] = (e & 0xffu) | (((e >> 8) * slot_bytes) << 8);
 			}
 		}
-		if (lp.gather_fold) run_gather_any<true>(g, isz, osz, gl, gi);
-		else run_gather_any<false>(g, isz, osz, gl, gi);
+		if (lp.gather_fold) { if (lp.gather_shift) run_gather_any<true, true>(g, isz, osz, gl, gi); else run_gather_any<true, false>(g, isz, osz, gl, gi); }
+		else { if (lp.gather_shift) run_gather_any<false, true>(g, isz, osz, gl, gi); else run_gather_any<false, false>(g, isz, osz, gl, gi); }
 	}
 	if (lp.any_general)
 		for (long long task = 0; task < lp.general.total_tasks; task++)
 			for (int lane = 0; lane < 32; lane++) process_task(lp.general, tab, (uint32_t)task, lane);
-	return (lp.any_fast ? 1 : 0) | (lp.any_general ? 2 : 0) | (lp.any_gather ? 4 : 0) | (lp.any_gather && lp.gather_fold ? 8 : 0);
+	return (lp.any_fast ? 1 : 0) | (lp.any_general ? 2 : 0) | (lp.any_gather ? 4 : 0) | (lp.any_gather && lp.gather_fold ? 8 : 0) | (lp.any_gather && lp.gather_shift ? 16 : 0);
 }
 
 // Launch planning of a whole-frame call, without running anything (host logic only): which kernel serves each

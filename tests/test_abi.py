@@ -177,3 +177,54 @@ def test_random_setter_sequences_match_the_reference(hw_lib):
         assert states_equal(hw_lib.state(), want) == [], trial
         if ref is not None:
             assert states_equal(ref.state(), want) == [], trial
+
+
+def test_pattern_lut_with_out_of_range_slots_is_accepted_then_refused_at_use(hw_lib, reference):
+    """The reference setter copies any table (vfgs_hw.c:333-337); an entry above slot 8 only matters when a sample
+    hits it (out-of-bounds read of pattern[2][9], vfgs_hw.c:218). The shim mirrors the table like the reference and
+    refuses to synthesise grain with it (VFGS_B200_ERR_STATE, no GPU needed), instead of aborting in the setter."""
+    from versatilefilmgrain_b200.api import VfgsError
+    hw_lib.reset(); reference.reset()
+    lut = np.arange(256, dtype=np.uint8)  # slots 0..15
+    hw_lib.vfgs_set_pattern_lut(1, lut); reference.vfgs_set_pattern_lut(1, lut)
+    assert states_equal(hw_lib.state(), reference.state()) == []
+    with pytest.raises(VfgsError, match="slot"):
+        hw_lib.add_grain_frames_device_ptr(0x1000, 0x2000, 1, 256, 144)
+    hw_lib.reset()
+
+
+def test_overlapping_buffers_are_classified_before_any_device_work(hw_lib):
+    """in == out (all planes identical) is in place; any other overlap of input and output planes -- output one frame
+    behind the input, only the chroma planes aliased, Cb written over Cr -- is refused with VFGS_B200_ERR_ARG.
+    The check needs no GPU: without one, legal calls get past it and fail with the CUDA error instead."""
+    import torch
+    from versatilefilmgrain_b200.api import Planes, VfgsError
+    hw_lib.reset()
+    w, h, n = 256, 144, 3
+    ys, cs = w * h * 2, (w // 2) * (h // 2) * 2  # power-on state: 8-bit ... set 10-bit 4:2:0 explicitly
+    hw_lib.vfgs_set_depth(10)
+    fb = ys + 2 * cs
+    base = 0x10000000
+
+    def planes(b):
+        return Planes(b, b + ys, b + ys + cs, 2 * w, w, fb)
+
+    def rc_of(pin, pout):
+        try:
+            hw_lib.add_grain_planes_device(pin, pout, n, w, h)
+        except VfgsError as e:
+            return int(str(e).split("error ")[1].split(":")[0])
+        return 0
+
+    ok = (0,) if torch.cuda.is_available() else (3,)  # VFGS_B200_ERR_CUDA without a device
+    if not torch.cuda.is_available():
+        assert rc_of(planes(base), planes(base)) in ok                    # in place
+        assert rc_of(planes(base), planes(base + n * fb)) in ok            # disjoint, back to back
+    assert rc_of(planes(base), planes(base + fb)) == 1                     # output one frame behind the input
+    assert rc_of(planes(base), planes(base + 64)) == 1                     # shifted by a few bytes
+    mixed = planes(base + 2 * n * fb); mixed.u = base + ys                 # only Cb aliases (exactly): in place for that plane
+    if not torch.cuda.is_available():
+        assert rc_of(planes(base), mixed) in ok
+    swapped = planes(base + 2 * n * fb); swapped.u = base + ys + cs        # Cb written over the input's Cr
+    assert rc_of(planes(base), swapped) == 1
+    hw_lib.reset()

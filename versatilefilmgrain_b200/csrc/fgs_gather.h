@@ -11,12 +11,16 @@
 //   * The neighbour GRAIN an edge filter needs (vfgs_hw.c:250-259 reads the unfiltered grain of the two samples
 //     on either side of a block edge) is no longer recomputed from the neighbour's input sample (a second LUT
 //     lookup + gather per lane and line, plus global loads for the warp's end lanes): the adjacent lane has just
-//     computed exactly that value, so it travels by ONE warp shuffle. To keep every exchange inside a warp the
-//     component's lane units are numbered flat (all stripes of a frame in one run, like the fast kernel) and
-//     16-sample blocks start a warp one unit early: a warp holds units 32q-1 .. 32q+30, so that the pairs
-//     (second half of block b, first half of block b+1) never straddle two warps. 8-sample blocks have an edge on
-//     both sides of every lane: there a warp holds 30 units plus one recomputed halo lane at either end.
-//   * Nothing reads a neighbour's INPUT sample any more, so components with 16-sample blocks run in place.
+//     computed exactly that value, so it travels by ONE warp shuffle. Only a warp's two end lanes still recompute
+//     their outer neighbour from its input sample (one predicated 2-byte global load per line, issued with the
+//     line loads). The component's lane units are numbered flat (all stripes of a frame in one run, like the
+//     fast kernel), 32 per warp, so that a warp's 512 bytes of a row start on a 512-byte boundary of the run.
+//   * SHIFT variant (in-place calls, 16-sample blocks): a warp holds units 32q-1 .. 32q+30, so that the pairs
+//     (second half of block b, first half of block b+1) never straddle two warps and NOTHING reads a neighbour's
+//     input sample, which another warp may already have overwritten in place. Measured 11 % slower than the
+//     aligned numbering (profiles/r02_gather_ab.md: the warp's row segment then starts 16 bytes before a 128-byte
+//     line, every warp-wide access touches a fifth line and both end sectors are written half by half), so it is
+//     only used where it saves the detour through a scratch buffer.
 //   * The block's random sign (vfgs_hw.c:218 "* s") is folded into WHICH COPY of the slots is read (FOLD: the
 //     table image carries the negated slots behind the plain ones; taken when no slot holds a -128 byte and the
 //     copies fit into shared memory, else the sign is applied by one multiply per sample).
@@ -36,7 +40,6 @@ namespace vfgs {
 #endif
 constexpr int kGatherLB = VFGS_GATHER_LB; // lines in flight per lane
 static_assert(kGatherLB >= 2, "both vertical-overlap lines of a block-row must fall into the first group of lines");
-constexpr int kGatherUnits8 = 30;         // units a warp stores when the blocks are 8 samples wide (+ 2 halo lanes)
 
 // ---- lane exchange -------------------------------------------------------------------------
 // Device: a warp shuffle. Host build (tests/emu runs the lanes one after the other): every task is run twice,
@@ -87,8 +90,10 @@ VFGS_HD uint32_t index_bits(const uint32_t raw[4])
 struct GatherLane {
 	smem_addr_t own;        // window of the lane's block: slot bank (sign copy with FOLD) + oy * pitch + ox + i0
 	smem_addr_t up;         // same for the block above (overlap lines only)
+	smem_addr_t nb, nb_up;  // end lanes of a warp: the outer neighbour's edge column in ITS block's windows
 	smem_addr_t lut;        // this lane's column of the component's private LUT
 	int s_own, s_up;        // block signs (applied by multiplication when !FOLD)
+	int s_nb, s_nb_up;
 	int pow16;
 	uint32_t lo2, hi2;
 };
@@ -119,6 +124,20 @@ VFGS_HD void gather_grain(const GatherLane& L, const uint32_t raw[4], int rc, in
 	gather_sample<IN16, FOLD, OVERLAP, 5>(L, raw, rc, ru, wc, wu, sc[5], g[5]);
 	gather_sample<IN16, FOLD, OVERLAP, 6>(L, raw, rc, ru, wc, wu, sc[6], g[6]);
 	gather_sample<IN16, FOLD, OVERLAP, 7>(L, raw, rc, ru, wc, wu, sc[7], g[7]);
+}
+
+// Unfiltered grain of the sample `v` next to a warp's end lane, from that sample's own intensity and its own block's
+// window (the value the neighbouring warp's end lane computes for itself).
+template <bool FOLD, bool OVERLAP>
+VFGS_HD int gather_neighbour(const GatherLane& L, uint32_t v, int in_shift, int rc, int ru, int w_cur, int w_up)
+{
+	const smem_addr_t off = (smem_addr_t)(lds32(L.lut | (smem_addr_t)(((v >> in_shift) & 0xffu) << 7)) >> 8);
+	int g = lds_s8(L.nb + rc + off);
+	if (OVERLAP) {
+		const int wc = FOLD ? w_cur : w_cur * L.s_nb, wu = FOLD ? w_up : w_up * L.s_nb_up;
+		g = (g * wc + lds_s8(L.nb_up + ru + off) * wu + 16) >> 5;
+	} else if (!FOLD) g *= L.s_nb;
+	return g;
 }
 
 // scale, add, clip (vfgs_hw.c:239, 260-267) and the optional 10 -> 8 bit conversion (yuv.c:231)
@@ -169,16 +188,46 @@ VFGS_HD smem_addr_t gather_window(smem_addr_t bank, int neg_off, uint32_t entry,
 	return bank + (smem_addr_t)((entry & 0x7fffu) + (uint32_t)col + (uint32_t)((FOLD && neg) ? neg_off : 0));
 }
 
-// One warp-task. NSH = 4: 16-sample blocks, lane = half a block, one edge per lane, the warp's 32 lanes are the flat
-// units 32 q - 1 .. 32 q + 30 of the component. NSH = 3: 8-sample blocks, lane = one block with an edge at both ends,
-// the warp's lanes 1 .. 30 are the flat units 30 q .. 30 q + 29 and lanes 0 / 31 recompute their neighbours (halo).
-// Units run over all stripes of a frame; rows are padded to an even number of units so that the parity of a unit is
-// the parity of its lane. Every lane walks the full line count of a stripe (the exchange is a warp-wide shuffle);
-// lanes outside the picture or past the end of a short last stripe neither load nor store.
-template <bool IN16, bool OUT8, int NSH, bool FOLD>
+// one sample (IB bytes wide) when pred is set, else 0; volatile so that it is issued where it is written (a batch
+// ahead of its use) instead of being sunk next to the use
+template <int IB>
+VFGS_HD uint32_t ld_sample_if(const uint8_t* p, bool pred)
+{
+#if defined(__CUDA_ARCH__)
+	uint32_t v = 0;
+	if (IB == 2)
+		asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.u16 %0, [%1];\n\t}" : "+r"(v) : "l"(p), "r"((uint32_t)pred));
+	else
+		asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.u8 %0, [%1];\n\t}" : "+r"(v) : "l"(p), "r"((uint32_t)pred));
+	return v;
+#else
+	if (!pred) return 0;
+	return IB == 2 ? (uint32_t)*(const uint16_t*)p : (uint32_t)*p;
+#endif
+}
+#ifndef VFGS_GATHER_PREFETCH
+#define VFGS_GATHER_PREFETCH 0 // lines ahead of the line loads that are prefetched into L1 (build-time knob for experiments)
+#endif
+VFGS_HD void prefetch_l1(const uint8_t* p, bool pred)
+{
+#if defined(__CUDA_ARCH__)
+	asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %1, 0;\n\t@q prefetch.global.L1 [%0];\n\t}" :: "l"(p), "r"((uint32_t)pred));
+#else
+	(void)p; (void)pred;
+#endif
+}
+
+// One warp-task: 32 consecutive flat lane units of a component (lane = 8 samples: half a 16-sample block with one
+// block edge, NSH = 4, or a whole 8-sample block with an edge at both ends, NSH = 3). Units run over all stripes of
+// a frame; rows are padded to an even number of units so that the parity of a unit is the parity of its lane.
+// SHIFT (NSH = 4 only): the warp holds units 32 q - 1 .. 32 q + 30 instead, see the head of this file.
+// Every lane walks the full line count of a stripe (the exchange is a warp-wide shuffle); lanes outside the picture
+// or past the end of a short last stripe neither load nor store.
+template <bool IN16, bool OUT8, int NSH, bool FOLD, bool SHIFT>
 VFGS_HD void gather_task_body(const FgsParams& p, smem_addr_t luts, smem_addr_t img, int f, int c, uint32_t q, int lane)
 {
 	constexpr bool PAIR = NSH == 4;
+	static_assert(PAIR || !SHIFT, "the shifted numbering exists for 16-sample blocks only");
 	constexpr int n = 1 << NSH;
 	constexpr int LB = kGatherLB;
 	const Plane& pl = p.comp[c];
@@ -186,7 +235,7 @@ VFGS_HD void gather_task_body(const FgsParams& p, smem_addr_t luts, smem_addr_t 
 	const int lines = 16 >> ysh;
 
 	// which unit is this lane
-	const long long u = PAIR ? (long long)q * 32 + lane - 1 : (long long)q * kGatherUnits8 + lane - 1;
+	const long long u = (long long)q * 32 + lane - (SHIFT ? 1 : 0);
 	const uint32_t upr = (uint32_t)p.gunits_per_row[c];                 // padded to even
 	bool valid = u >= 0 && u < (long long)upr * (uint32_t)p.rows;
 	const uint32_t uu = valid ? (uint32_t)u : 0u;
@@ -205,20 +254,31 @@ VFGS_HD void gather_task_body(const FgsParams& p, smem_addr_t luts, smem_addr_t 
 	const long long in_pitch = pl.in_row_bytes, out_pitch = pl.out_row_bytes;
 	const uint8_t* src = pl.in + (long long)f * p.in_frame_bytes + (long long)cl0 * in_pitch + (long long)k0 * IB;
 	uint8_t* dst = pl.out + (long long)f * p.out_frame_bytes + (long long)cl0 * out_pitch + (long long)k0 * OB;
-	const bool stores = lane_stores() && (PAIR || (lane >= 1 && lane <= kGatherUnits8));
-
-	uint32_t raw[LB][4] = {};
-#pragma unroll
-	for (int qq = 0; qq < LB; qq++) {
-		if (IN16) ld_global_16_if(src + qq * in_pitch, raw[qq], qq < nl);
-		else ld_global_8_if(src + qq * in_pitch, raw[qq], qq < nl);
-	}
+	const bool stores = lane_stores();
 
 	const int b = valid ? (k0 >> NSH) : 0; // idle lanes must not index past the table row
 	const int i0 = k0 & (n - 1);
 	const bool has_left = valid && (i0 == 0) && (b > 0);
 	const bool has_right = valid && (i0 + kSamplesPerLane == n) && (b + 1 < p.nb);
 	const bool odd = i0 != 0; // PAIR: second half of a block, its one edge is on the right
+	// a warp's end lanes fetch their outer neighbour's sample from memory (never with SHIFT: every pair is inside a warp);
+	// the host build runs lane by lane with the same rule
+	const bool mem_left = !SHIFT && lane == 0 && has_left;
+	const bool mem_right = !SHIFT && lane == 31 && has_right && k0 + kSamplesPerLane < pl.width; // samples right of the picture read as 0
+	const bool mem_halo = mem_left || mem_right;
+	const long long halo_off = mem_right ? (long long)kSamplesPerLane * IB : -(long long)IB;
+
+	uint32_t raw[LB][4] = {}, vh[LB];
+#pragma unroll
+	for (int qq = 0; qq < LB; qq++) {
+		if (IN16) ld_global_16_if(src + qq * in_pitch, raw[qq], qq < nl);
+		else ld_global_8_if(src + qq * in_pitch, raw[qq], qq < nl);
+		vh[qq] = SHIFT ? 0u : ld_sample_if<IB>(src + qq * in_pitch + halo_off, mem_halo && qq < nl);
+	}
+	if (VFGS_GATHER_PREFETCH > 0) {
+#pragma unroll
+		for (int qq = LB; qq < LB + VFGS_GATHER_PREFETCH; qq++) prefetch_l1(src + qq * in_pitch, qq < nl);
+	}
 
 	const int bank = c ? 1 : 0;
 	const int stride = p.pat_stride[bank];
@@ -233,9 +293,14 @@ VFGS_HD void gather_task_body(const FgsParams& p, smem_addr_t luts, smem_addr_t 
 	const smem_addr_t bank_addr = img + (smem_addr_t)p.gpat_off[bank];
 	const int neg_off = p.gneg_off[bank];
 	L.own = gather_window<FOLD>(bank_addr, neg_off, w_cur[0], i0, L.s_own);
-	L.up = L.own; L.s_up = 1;
+	L.up = L.nb = L.nb_up = L.own; L.s_up = L.s_nb = L.s_nb_up = 1;
 	const bool ovl = valid && r > 0; // the first lines of a stripe overlap the block-row above (never in the first stripe, y <= 15)
 	if (ovl) L.up = gather_window<FOLD>(bank_addr, neg_off, (w_cur - p.spitch * 4)[0], i0, L.s_up);
+	if (!SHIFT && mem_halo) { // the neighbouring block's window: its last column (left neighbour) or its first (right neighbour)
+		const int nbo = mem_right ? 4 : -4, col = mem_right ? 0 : n - 1;
+		L.nb = gather_window<FOLD>(bank_addr, neg_off, w_cur[nbo], col, L.s_nb);
+		if (ovl) L.nb_up = gather_window<FOLD>(bank_addr, neg_off, (w_cur - p.spitch * 4)[nbo], col, L.s_nb_up);
+	}
 
 	// exchange partner of a 16-sample-block lane: the other side of its one block edge
 	const int partner = odd ? lane + 1 : lane - 1;
@@ -248,27 +313,33 @@ VFGS_HD void gather_task_body(const FgsParams& p, smem_addr_t luts, smem_addr_t 
 #pragma unroll
 		for (int qq = 0; qq < LB; qq++) {
 			const int line = base + qq;
-			int g[8], sc[8];
+			int g[8], sc[8], gh = 0;
 			bool done = false;
 			if (FIRST && qq < 2 && !(qq == 1 && ysh)) { // vfgs_hw.c:173-188: lines 0 and 1 (line 0 only for vertically subsampled chroma)
 				if (ovl) { // per lane: a warp may hold the end of the first stripe and the start of the second
 					const int w_c = qq == 0 ? (ysh ? 20 : 12) : 24, w_u = qq == 0 ? (ysh ? 20 : 24) : 12;
 					const int ru = ((16 + qq) >> ysh) * stride;
 					gather_grain<IN16, FOLD, true>(L, raw[qq], rc, ru, w_c, w_u, g, sc);
+					if (!SHIFT) gh = gather_neighbour<FOLD, true>(L, vh[qq], p.bs, rc, ru, w_c, w_u);
 					done = true;
 				}
 			}
-			if (!done) gather_grain<IN16, FOLD, false>(L, raw[qq], rc, 0, 0, 0, g, sc);
+			if (!done) {
+				gather_grain<IN16, FOLD, false>(L, raw[qq], rc, 0, 0, 0, g, sc);
+				if (!SHIFT) gh = gather_neighbour<FOLD, false>(L, vh[qq], p.bs, rc, 0, 0, 0);
+			}
 
 			// block-edge filter (vfgs_hw.c:250-259): both sides read the unfiltered grain of the other side
 			if (PAIR) {
-				const int got = lane_exchange(odd ? g[7] : g[0], partner);
+				int got = lane_exchange(odd ? g[7] : g[0], partner);
+				if (!SHIFT) got = mem_halo ? gh : got;
 				const int a = odd ? g[7] : g[0], bb = odd ? g[6] : g[1];
 				const int fl = (got + 3 * a + bb + 2) >> 2;
 				g[0] = has_left ? fl : g[0];
 				g[7] = has_right ? fl : g[7];
 			} else {
-				const int gl = lane_exchange(g[7], lane - 1), gr = lane_exchange(g[0], lane + 1);
+				int gl = lane_exchange(g[7], lane - 1), gr = lane_exchange(g[0], lane + 1);
+				gl = mem_left ? gh : gl; gr = mem_right ? gh : gr;
 				const int f0 = (gl + 3 * g[0] + g[1] + 2) >> 2;
 				const int f7 = (g[6] + 3 * g[7] + gr + 2) >> 2;
 				g[0] = has_left ? f0 : g[0];
@@ -279,6 +350,8 @@ VFGS_HD void gather_task_body(const FgsParams& p, smem_addr_t luts, smem_addr_t 
 			const bool more = line + LB < nl;
 			if (IN16) ld_global_16_if(nxt, raw[qq], more);
 			else ld_global_8_if(nxt, raw[qq], more);
+			if (!SHIFT) vh[qq] = ld_sample_if<IB>(nxt + halo_off, mem_halo && more);
+			if (VFGS_GATHER_PREFETCH > 0) prefetch_l1(nxt + VFGS_GATHER_PREFETCH * in_pitch, line + LB + VFGS_GATHER_PREFETCH < nl);
 			if (line < nl && stores) {
 				if (OB == 2) st_global_16(dst, w);
 				else st_global_8(dst, w);
@@ -292,8 +365,8 @@ VFGS_HD void gather_task_body(const FgsParams& p, smem_addr_t luts, smem_addr_t 
 }
 
 // Gather-kernel task numbering: per frame the gather components one after the other, each cut into warp-tasks of
-// 32 (16-sample blocks) or 30 (8-sample blocks) consecutive flat units.
-template <bool IN16, bool OUT8, bool FOLD>
+// 32 consecutive flat units.
+template <bool IN16, bool OUT8, bool FOLD, bool SHIFT>
 VFGS_HD void process_task_gather(const FgsParams& p, smem_addr_t luts, smem_addr_t img, uint32_t task, int lane)
 {
 	const int f = (int)fastdiv(task, p.div_gtasks);
@@ -304,8 +377,9 @@ VFGS_HD void process_task_gather(const FgsParams& p, smem_addr_t luts, smem_addr
 #if !defined(__CUDA_ARCH__)
 	emu_warp().lane = lane; emu_warp().point = 0;
 #endif
-	if (c && p.subx > 1) gather_task_body<IN16, OUT8, 3, FOLD>(p, luts, img, f, c, q, lane);
-	else gather_task_body<IN16, OUT8, 4, FOLD>(p, luts, img, f, c, q, lane);
+	if (SHIFT) gather_task_body<IN16, OUT8, 4, FOLD, true>(p, luts, img, f, c, q, lane); // the host never sends 8-sample blocks here
+	else if (c && p.subx > 1) gather_task_body<IN16, OUT8, 3, FOLD, false>(p, luts, img, f, c, q, lane);
+	else gather_task_body<IN16, OUT8, 4, FOLD, false>(p, luts, img, f, c, q, lane);
 }
 
 } // namespace vfgs

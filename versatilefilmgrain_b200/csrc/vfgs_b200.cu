@@ -37,7 +37,7 @@ struct Context {
 	int device = -1;
 	int sm_count = 0;
 	int max_smem_optin = 0;
-	int fast_pad = 0;           // gap between the fast kernel's dynamic shared memory and the next 32 KB boundary
+	int fast_pad = 0;           // gap between the fast kernel's dynamic shared memory and the next 32 KB boundary (measured by a probe launch)
 	uint32_t* d_pow2 = nullptr;
 	uint8_t* d_blob = nullptr;
 	size_t blob_cap = 0;
@@ -137,16 +137,25 @@ int ensure_ctx(int device)
 	c.device = device;
 	c.sm_count = prop.multiProcessorCount;
 	c.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
-	{ // where the fast kernel's dynamic shared memory starts inside the shared window: behind the driver's
-	  // reserved bytes and the kernel's static variables (the kernel traps if this guess is off)
-		int reserved = 0;
-		CUDA_TRY(cudaDeviceGetAttribute(&reserved, cudaDevAttrReservedSharedMemoryPerBlock, device));
-		cudaFuncAttributes fa;
-		CUDA_TRY(cudaFuncGetAttributes(&fa, fgs_apply_fast_kernel<true, false>));
-		const int base = reserved + ((int)fa.sharedSizeBytes + 127) / 128 * 128;
-		c.fast_pad = (kLutAlign - base % kLutAlign) % kLutAlign;
-	}
 	CUDA_TRY(cudaMalloc(&c.d_pow2, sizeof(uint32_t) * kJumpBits * 32));
+	{ // where the fast kernel's dynamic shared memory starts inside the shared window (behind the driver's reserved
+	  // bytes and the kernel's static variables): asked of each variant by a one-thread probe launch, because the
+	  // host lays the table images out for exactly that gap in front of the first LUT
+		uint32_t* d_probe = (uint32_t*)c.d_pow2; // scratch: the jump table is uploaded right after
+		FgsParams pp;
+		memset(&pp, 0, sizeof(pp));
+		pp.probe = d_probe;
+		fgs_apply_fast_kernel<true, false><<<1, 32, 1024>>>(pp);
+		pp.probe = d_probe + 1;
+		fgs_apply_fast_kernel<true, true><<<1, 32, 1024>>>(pp);
+		pp.probe = d_probe + 2;
+		fgs_apply_fast_kernel<false, false><<<1, 32, 1024>>>(pp);
+		uint32_t pads[3] = {0, 0, 0};
+		CUDA_TRY(cudaMemcpy(pads, d_probe, sizeof(pads), cudaMemcpyDeviceToHost));
+		if (pads[0] != pads[1] || pads[0] != pads[2])
+			return set_err(VFGS_B200_ERR_CUDA, "fast kernel variants place dynamic shared memory differently (%u, %u, %u)", pads[0], pads[1], pads[2]);
+		c.fast_pad = (int)pads[0];
+	}
 	CUDA_TRY(cudaMemcpy(c.d_pow2, jump_table().pow2, sizeof(uint32_t) * kJumpBits * 32, cudaMemcpyHostToDevice));
 	CUDA_TRY(cudaStreamCreateWithFlags(&c.s_h2d, cudaStreamNonBlocking));
 	CUDA_TRY(cudaStreamCreateWithFlags(&c.s_k, cudaStreamNonBlocking));
@@ -219,6 +228,10 @@ int make_geometry(Geometry& g, int width, int height, int out_depth)
 	if (h.scale_shift + h.bs < 8 || h.scale_shift + h.bs > 13)
 		return set_err(VFGS_B200_ERR_STATE, "scale_shift %d + bs %d outside 8..13 (vfgs_hw.c:170)", h.scale_shift, h.bs);
 	if (height < 1) return set_err(VFGS_B200_ERR_ARG, "height %d", height);
+	for (int c = 0; c < 3; c++)
+		for (int i = 0; i < 256; i++)
+			if ((h.plut[c][i] >> 4) >= kSlots)
+				return set_err(VFGS_B200_ERR_STATE, "pattern LUT %d entry %d selects slot %d: the hardware has slots 0..8 (vfgs_hw.c:49,218)", c, i, h.plut[c][i] >> 4);
 	g.in_depth = 8 + h.bs;
 	g.out_depth = out_depth ? out_depth : g.in_depth;
 	if (g.out_depth != g.in_depth && !(g.out_depth == 8 && g.in_depth == 10))
@@ -247,14 +260,20 @@ void fill_common(FgsParams& p, const Geometry& g)
 typedef void (*GrainKernel)(const FgsParams);
 enum KernelKind { kGeneral = 0, kFast = 1, kGather = 2 };
 
-template <bool FOLD>
+template <bool FOLD, bool SHIFT>
 GrainKernel gather_kernel(const FgsParams& p)
 {
-	return p.in_bytes == 1 ? fgs_apply_gather_kernel<false, false, FOLD>
-	     : p.out_bytes == 1 ? fgs_apply_gather_kernel<true, true, FOLD> : fgs_apply_gather_kernel<true, false, FOLD>;
+	return p.in_bytes == 1 ? fgs_apply_gather_kernel<false, false, FOLD, SHIFT>
+	     : p.out_bytes == 1 ? fgs_apply_gather_kernel<true, true, FOLD, SHIFT> : fgs_apply_gather_kernel<true, false, FOLD, SHIFT>;
+}
+GrainKernel gather_kernel(const FgsParams& p, bool fold, bool shift)
+{
+	return fold ? (shift ? gather_kernel<true, true>(p) : gather_kernel<true, false>(p))
+	            : (shift ? gather_kernel<false, true>(p) : gather_kernel<false, false>(p));
 }
 
-int launch_apply(const FgsParams& p, cudaStream_t stream, KernelKind kind = kGeneral, int gather_smem = 0, bool gather_fold = false)
+int launch_apply(const FgsParams& p, cudaStream_t stream, KernelKind kind = kGeneral, int gather_smem = 0, bool gather_fold = false,
+                 bool gather_shift = false)
 {
 	Context& c = g_ctx;
 	if (p.total_tasks <= 0) return VFGS_B200_OK;
@@ -272,15 +291,15 @@ int launch_apply(const FgsParams& p, cudaStream_t stream, KernelKind kind = kGen
 			c.fast_smem_attr = smem;
 		}
 	} else if (kind == kGather) {
-		kern = gather_fold ? gather_kernel<true>(p) : gather_kernel<false>(p);
+		kern = gather_kernel(p, gather_fold, gather_shift);
 		threads = kGatherThreads; smem = gather_smem;
 		if (smem > c.gather_smem_attr) {
-			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_gather_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_gather_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_gather_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_gather_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_gather_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_gather_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+			FgsParams v = p; // every variant of the gather kernel
+			for (int io = 0; io < 3; io++) {
+				v.in_bytes = io == 0 ? 1 : 2; v.out_bytes = io == 2 ? 2 : 1;
+				for (int fs = 0; fs < 4; fs++)
+					CUDA_TRY(cudaFuncSetAttribute(gather_kernel(v, (fs & 1) != 0, (fs & 2) != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+			}
 			c.gather_smem_attr = smem;
 		}
 	}
@@ -395,7 +414,7 @@ int run_frames_device(const vfgs_b200_planes& in, const vfgs_b200_planes& out, i
 	if (lp.any_fast)
 		if (int rc = launch_apply(lp.fast, stream, kFast)) return rc;
 	if (lp.any_gather)
-		if (int rc = launch_apply(lp.gather, stream, kGather, lp.gather_smem, lp.gather_fold)) return rc;
+		if (int rc = launch_apply(lp.gather, stream, kGather, lp.gather_smem, lp.gather_fold, lp.gather_shift)) return rc;
 	if (lp.any_general)
 		if (int rc = launch_apply(lp.general, stream, kGeneral)) return rc;
 	return VFGS_B200_OK;
@@ -403,23 +422,57 @@ int run_frames_device(const vfgs_b200_planes& in, const vfgs_b200_planes& out, i
 
 // How the output planes lie relative to the input planes: 0 disjoint, 1 in place (every overlapping plane pair is
 // the same plane with the same strides and sample size), -1 anything else (partial overlap: not supported).
+// Planes of consecutive frames interleave in memory (Y0 U0 V0 Y1 ...), so plane pairs are compared frame by frame in
+// closed form: with a common frame stride S, frame f1 of one plane meets frame f2 of the other iff their byte
+// extents overlap for some k = f1 - f2 within the batch.
 int aliasing(const vfgs_b200_planes& in, const vfgs_b200_planes& out, int n, const Geometry& g)
 {
 	const uint8_t* ip[3] = {(const uint8_t*)in.y, (const uint8_t*)in.u, (const uint8_t*)in.v};
 	const uint8_t* op[3] = {(const uint8_t*)out.y, (const uint8_t*)out.u, (const uint8_t*)out.v};
-	auto extent = [&](const vfgs_b200_planes& pl, int c, size_t sample) {
+	auto extent = [&](const vfgs_b200_planes& pl, int c, size_t sample) { // bytes one frame's plane spans
 		const int64_t lines = c ? g.ch : g.height, width = c ? g.cw : g.width;
 		if (lines < 1 || width < 1) return (int64_t)0;
-		return (int64_t)(n - 1) * pl.frame_stride + (lines - 1) * (c ? pl.stride_c : pl.stride_y) + width * (int64_t)sample;
+		return (lines - 1) * (c ? pl.stride_c : pl.stride_y) + width * (int64_t)sample;
 	};
+	// bounding ranges of the two calls' buffers
+	const uint8_t *ilo = nullptr, *ihi = nullptr, *olo = nullptr, *ohi = nullptr;
+	for (int c = 0; c < 3; c++) {
+		const int64_t ei = extent(in, c, g.in_sample), eo = extent(out, c, g.out_sample);
+		if (ei > 0) {
+			const uint8_t* e = ip[c] + (int64_t)(n - 1) * in.frame_stride + ei;
+			if (!ilo || ip[c] < ilo) ilo = ip[c];
+			if (!ihi || e > ihi) ihi = e;
+		}
+		if (eo > 0) {
+			const uint8_t* e = op[c] + (int64_t)(n - 1) * out.frame_stride + eo;
+			if (!olo || op[c] < olo) olo = op[c];
+			if (!ohi || e > ohi) ohi = e;
+		}
+	}
+	if (!ilo || !olo || ihi <= olo || ohi <= ilo) return 0;
+	if (n > 1 && in.frame_stride != out.frame_stride) return -1; // overlapping buffers walked with different strides
+	const int64_t S = in.frame_stride;
 	int result = 0;
 	for (int i = 0; i < 3; i++)
 		for (int j = 0; j < 3; j++) {
 			const int64_t ei = extent(in, i, g.in_sample), ej = extent(out, j, g.out_sample);
 			if (ei <= 0 || ej <= 0) continue;
-			if (ip[i] + ei <= op[j] || op[j] + ej <= ip[i]) continue; // disjoint byte ranges
-			const bool same = i == j && ip[i] == op[j] && g.in_sample == g.out_sample && in.frame_stride == out.frame_stride &&
+			const bool same = i == j && ip[i] == op[j] && g.in_sample == g.out_sample &&
 			                  (i ? in.stride_c == out.stride_c : in.stride_y == out.stride_y);
+			bool hit;
+			if (n > 1 && S > 0) {
+				// frame f1 of the input plane against frame f2 of the output plane: [f1 S, f1 S + ei) meets [D + f2 S, D + f2 S + ej)
+				// iff D - ei < k S < D + ej for k = f1 - f2, |k| <= n - 1
+				const int64_t D = (int64_t)(op[j] - ip[i]);
+				auto floor_div = [](int64_t a, int64_t b) { int64_t q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; };
+				int64_t k_lo = floor_div(D - ei, S) + 1, k_hi = -floor_div(-(D + ej), S) - 1;
+				if (k_lo < -(int64_t)(n - 1)) k_lo = -(int64_t)(n - 1);
+				if (k_hi > (int64_t)(n - 1)) k_hi = (int64_t)(n - 1);
+				hit = k_lo <= k_hi;
+			} else {
+				hit = !(ip[i] + ei <= op[j] || op[j] + ej <= ip[i]);
+			}
+			if (!hit) continue;
 			if (!same) return -1;
 			result = 1;
 		}
@@ -433,8 +486,6 @@ void packed_planes(vfgs_b200_planes& pl, const void* base, const Geometry& g, si
 	pl.stride_y = (int64_t)(g.width * sample); pl.stride_c = (int64_t)(g.cw * sample);
 	pl.frame_stride = (int64_t)frame_bytes;
 }
-
-bool all_uniform() { return g_bi.uniform_pi[0] >= 0 && g_bi.uniform_pi[1] >= 0 && g_bi.uniform_pi[2] >= 0; }
 
 int prepare(int device)
 {
@@ -477,8 +528,9 @@ void vfgs_set_pattern_lut(int c, uint8_t lut[]) // vfgs_hw.c:333-337
 {
 	pipe_before_state_change();
 	REQUIRE(c >= 0 && c < 3);
-	// lut[i] >> 4 indexes pattern[..][9] in vfgs_hw.c:218; anything above slot 8 is out of bounds there
-	for (int i = 0; i < 256; i++) REQUIRE((lut[i] >> 4) < kSlots);
+	// Any table is accepted, like the reference does (vfgs_hw.c:333-337). lut[i] >> 4 indexes pattern[..][9] in
+	// vfgs_hw.c:218: an entry above slot 8 makes the reference read out of bounds if a sample ever hits it; here
+	// such a table is refused when grain is requested (make_geometry: VFGS_B200_ERR_STATE), not in the setter.
 	memcpy(hw().plut[c], lut, 256);
 	g_dirty = true;
 }
@@ -621,12 +673,12 @@ int vfgs_b200_add_grain_planes_device(const vfgs_b200_planes* in, const vfgs_b20
 	if (!in || !out || nframes < 0) return set_err(VFGS_B200_ERR_ARG, "null planes or negative frame count");
 	Geometry g;
 	if (int rc = make_geometry(g, width, height, out_depth)) return rc;
-	if (int rc = prepare(-1)) return rc;
-	if (nframes == 0) return VFGS_B200_OK;
-	const int alias = aliasing(*in, *out, nframes, g);
+	const int alias = nframes ? aliasing(*in, *out, nframes, g) : 0; // argument check first: needs no device
 	if (alias < 0)
 		return set_err(VFGS_B200_ERR_ARG, g.in_depth != g.out_depth ? "in-place needs equal depths"
 		               : "input and output planes overlap without being identical (same planes, strides and depth)");
+	if (int rc = prepare(-1)) return rc;
+	if (nframes == 0) return VFGS_B200_OK;
 	const bool in_place = alias == 1;
 	Context& c = g_ctx;
 	cudaStream_t st = (cudaStream_t)stream;

@@ -187,7 +187,8 @@ struct FgsParams {
 	int fimg_src[3];        // byte offset of the component's image inside fblob
 	int fimg_bytes[3];      // its size (0: the component is not served by the fast kernel)
 	int fimg_off[3];        // where it goes in shared memory, relative to the first LUT (negative: in front of it)
-	int fpad;               // bytes between the start of dynamic shared memory and the first LUT (checked by the kernel)
+	int fpad;               // bytes between the start of dynamic shared memory and the first LUT (measured by a probe launch)
+	uint32_t* probe;        // not null: the fast kernel only reports that gap here and returns (vfgs_b200.cu, ensure_ctx)
 	int fsmem;              // dynamic shared memory of the launch
 	int fpat_off[3][2];     // +pattern / -pattern copies, relative to the component's image
 	int fpat_stride[3];

@@ -161,9 +161,15 @@ fgs_apply_fast_kernel(const __grid_constant__ FgsParams p)
 	extern __shared__ __align__(128) uint8_t smem[];
 	__shared__ __align__(8) uint64_t bar;
 
-	// the host laid the images out for the gap it expects in front of the first LUT
+	// the host laid the images out for the gap in front of the first LUT, which it measured with a probe launch
 	const uint32_t pad = (0u - smem_u32(smem)) & (uint32_t)(kLutAlign - 1);
+	if (p.probe) {
+		if (threadIdx.x == 0) *p.probe = pad;
+		return;
+	}
+#ifdef VFGS_DEBUG_ASSERTS
 	if (pad != (uint32_t)p.fpad) __trap();
+#endif
 	uint8_t* lut_ptr = smem + pad;
 
 	if (threadIdx.x == 0) mbar_init(&bar, 1);
@@ -196,7 +202,7 @@ constexpr int kGatherThreads = VFGS_GATHER_THREADS; // one CTA per SM at up to 7
                                                     // measured ahead of 2 x 384 (one table image per SM) and of 640-832 and 960-1024 threads
 constexpr int kGatherWarps = kGatherThreads / 32;
 
-template <bool IN16, bool OUT8, bool FOLD>
+template <bool IN16, bool OUT8, bool FOLD, bool SHIFT>
 __global__ void __launch_bounds__(kGatherThreads, VFGS_GATHER_CTAS)
 fgs_apply_gather_kernel(const __grid_constant__ FgsParams p)
 {
@@ -229,7 +235,7 @@ fgs_apply_gather_kernel(const __grid_constant__ FgsParams p)
 	const smem_addr_t luts = smem_addr(lut_ptr), img = smem_addr(img_ptr);
 	const long long stride = (long long)gridDim.x * kGatherWarps;
 	for (long long task = (long long)blockIdx.x * kGatherWarps + (threadIdx.x >> 5); task < p.total_tasks; task += stride)
-		process_task_gather<IN16, OUT8, FOLD>(p, luts, img, (uint32_t)task, lane);
+		process_task_gather<IN16, OUT8, FOLD, SHIFT>(p, luts, img, (uint32_t)task, lane);
 }
 
 } // namespace vfgs

@@ -245,6 +245,7 @@ struct LaunchPlan {
 	int kind[3];     // per component: 0 fast, 1 gather, 2 general kernel
 	int gather_smem; // dynamic shared memory of the gather launch
 	bool gather_fold; // the gather launch reads sign-folded slot copies (fgs_gather.h, FOLD)
+	bool gather_shift; // in-place call: the gather launch uses the shifted unit numbering (fgs_gather.h, SHIFT)
 };
 
 inline void plan_launches(const FgsParams& p, const TableInfo& bi, int mode, bool in_place, int smem_limit, int fast_pad, LaunchPlan& lp)
@@ -257,8 +258,9 @@ inline void plan_launches(const FgsParams& p, const TableInfo& bi, int mode, boo
 		const bool aligned = p.comp[c].vec && (p.comp[c].width % kSamplesPerLane) == 0;
 		kind[c] = 2;
 		if (aligned && mode != 1) {
-			// in place: the gather kernel's 8-sample-block lanes recompute their warp neighbours from INPUT samples
-			// another warp may already have overwritten; 16-sample-block lanes read nothing but their own samples
+			// in place: the gather kernel's shifted numbering (SHIFT) reads nothing but a lane's own samples, but exists for
+			// 16-sample blocks only; the aligned numbering recomputes the warps' outer neighbours from INPUT samples
+			// another warp may already have overwritten
 			const bool block8 = c && p.subx > 1;
 			if (bi.fast_ok[c] && mode != 2) kind[c] = 0;
 			else if (!in_place || !block8) kind[c] = 1;
@@ -310,6 +312,7 @@ inline void plan_launches(const FgsParams& p, const TableInfo& bi, int mode, boo
 		}
 		f.div_ftasks = make_fastdiv((uint32_t)(f.ftasks_per_frame > 0 ? f.ftasks_per_frame : 1));
 	}
+	lp.gather_shift = in_place && ngather > 0;
 	lp.gather.ngather = ngather;
 	lp.gather.gpat_off[0] = bi.pat_off[0]; lp.gather.gpat_off[1] = bi.pat_off[1];
 	lp.gather.gneg_off[0] = bi.neg_off[0]; lp.gather.gneg_off[1] = bi.neg_off[1];
@@ -322,7 +325,8 @@ inline void plan_launches(const FgsParams& p, const TableInfo& bi, int mode, boo
 			const int upr = kind[c] == 1 ? ((g.comp[c].width + kSamplesPerLane - 1) / kSamplesPerLane + 1) & ~1 : 0;
 			const long long units = (long long)upr * g.rows;
 			g.gunits_per_row[c] = upr;
-			g.gtasks[c] = kind[c] != 1 ? 0 : block8 ? (int)((units + kGatherUnits8 - 1) / kGatherUnits8) : (int)((units + 1 + 31) / 32);
+			(void)block8;
+			g.gtasks[c] = kind[c] != 1 ? 0 : (int)((units + (lp.gather_shift ? 1 : 0) + 31) / 32);
 			g.gtasks_per_frame += g.gtasks[c];
 			g.div_gunits[c] = make_fastdiv((uint32_t)(upr > 0 ? upr : 1));
 		}

@@ -29,7 +29,8 @@ def one_case(emu, rng):
             int(rng.integers(0, 2)), int(rng.integers(2, 8)), bool(rng.integers(0, 4) == 0))
     w = int(rng.choice(WIDTHS)); h = max(2, int(rng.integers(1, 70))); n = int(rng.integers(1, 4))
     for od in ((0, 8) if depth == 10 else (0,)):
-        frames = synth_frames(n, w, h, fmt, depth, seed=spec[0] % 1000)
+        kind = "natural" if rng.integers(0, 3) == 0 else "uniform"  # smooth frames exercise the gather code's octet path
+        frames = synth_frames(n, w, h, fmt, depth, seed=spec[0] % 1000, kind=kind)
         if depth == 10 and rng.integers(0, 3) == 0:
             frames = rng.integers(0, 65536, size=frames.size, dtype=np.uint16)  # codes far outside 10 bits
         o = Oracle(); program_random_state(o, *spec)

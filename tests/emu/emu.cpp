@@ -52,6 +52,8 @@ void run_gather_any(const FgsParams& g, size_t isz, size_t osz, const uint8_t* g
 } // namespace
 
 extern "C" int emu_state_size(void) { return (int)sizeof(StateDump); }
+// lane-lines of the gather task code that took the uniform-slot octet path since the last call (fgs_gather.h)
+extern "C" long long emu_octet_lines(void) { const long long v = emu_warp().octet_lines; emu_warp().octet_lines = 0; return v; }
 
 // Packed planar frames, whole frames, like vfgs_b200_add_grain_frames_device.
 // mode: 0 automatic kernel choice, 1 general task code everywhere, 2 gather task code wherever it can
@@ -221,4 +223,51 @@ extern "C" void emu_plan(const void* state, int width, int height, int out_depth
 	for (int c = 0; c < 3; c++) out[k++] = lp.fast.fwide[c];
 	for (int c = 0; c < 3; c++) out[k++] = lp.fast.funits_per_row[c];
 	out[k++] = lp.gather_smem;
+}
+
+// ---- firmware layer (fw_host.h + fw_device.h run with one host thread) ---------------------------
+#include "../../versatilefilmgrain_b200/csrc/fw_host.h"
+
+// What vfgs_b200_init_sei / vfgs_b200_init_afgs1 do, on a freshly powered-on hardware state with the given depth and
+// chroma subsampling (vfgs_main.c:750-757); the setters' arithmetic is restated from vfgs_hw.c:339-380 (test tool).
+// cfg: raw fgs_sei / fgs_afgs1 bytes. state_out: StateDump. Returns 0, or 1 where the reference asserts.
+extern "C" int emu_fw_init(const void* cfg, int is_afgs1, int depth, int csubx, int csuby, void* state_out)
+{
+	static HwState h; // 73 KB
+	h.power_on();
+	const int nbs = depth - 8;
+	h.scale_shift = (h.scale_shift + h.bs - nbs) & 0xff; h.bs = nbs; // vfgs_set_depth
+	h.csubx = csubx; h.csuby = csuby;
+	FwPlan plan;
+	if (is_afgs1) fw_plan_afgs1(*(const fgs_afgs1*)cfg, csubx, csuby, plan);
+	else fw_plan_sei(*(const fgs_sei*)cfg, csubx, csuby, plan);
+	if (plan.error) return 1;
+	static FwTables tables;
+	static bool have_tables = false;
+	if (!have_tables) { make_fw_tables(tables); have_tables = true; }
+	static FwScratch scratch;
+	memset(&scratch, 0, sizeof(scratch));
+	for (const FwJob& j : plan.jobs) fw_run_job_serial(j, tables, scratch, &h.pattern[0][0][0][0]);
+	memcpy(h.slut, plan.slut, sizeof(h.slut));
+	memcpy(h.plut, plan.plut, sizeof(h.plut));
+	if (plan.set_seed) h.rnd = h.rnd_up = h.line_rnd = h.line_rnd_up = plan.seed << 1;
+	if (plan.scale_shift < 2 || plan.scale_shift >= 8) return 1; // vfgs_hw.c:348
+	h.scale_shift = plan.scale_shift + 6 - h.bs;
+	if (plan.set_legal) { h.y_min = h.c_min = plan.legal ? 16 : 0; h.y_max = plan.legal ? 235 : 255; h.c_max = plan.legal ? 240 : 255; }
+	StateDump& d = *(StateDump*)state_out;
+	memcpy(d.pattern, h.pattern, sizeof(d.pattern));
+	memcpy(d.slut, h.slut, sizeof(d.slut));
+	memcpy(d.plut, h.plut, sizeof(d.plut));
+	d.rnd = h.rnd; d.rnd_up = h.rnd_up; d.line_rnd = h.line_rnd; d.line_rnd_up = h.line_rnd_up;
+	d.scale_shift = h.scale_shift; d.bs = h.bs; d.y_min = h.y_min; d.y_max = h.y_max; d.c_min = h.c_min; d.c_max = h.c_max;
+	d.csubx = h.csubx; d.csuby = h.csuby;
+	return 0;
+}
+
+extern "C" void emu_fw_tables(int8_t* gauss, int8_t* dct)
+{
+	FwTables t;
+	make_fw_tables(t);
+	memcpy(gauss, t.gauss, sizeof(t.gauss));
+	memcpy(dct, t.dct, sizeof(t.dct));
 }

@@ -96,6 +96,24 @@ def test_in_place_with_sample_adaptive_patterns(hw, case):
     assert hw.get_lfsr() == o.get_lfsr()
 
 
+@pytest.mark.parametrize("case", ["fgs_sei.cfg|d10|420|g100", "fgs_sei.cfg|d8|420|g100", "fgs_sei_ff_test5.cfg|d10|420|g100",
+                                  "fgs_sei_ff_test7.cfg|d10|420|g100"])
+def test_smooth_pictures(hw, case):
+    """Natural-looking frames (smooth gradient + noise): most lanes of the gather kernel see one pattern slot per eight
+    samples and take its word-fetch path, some do not (mixed warps); out of place, fused 10 -> 8, and in place."""
+    meta = G.cases[case]
+    w, h, n = 1920, 136, 2
+    frames = synth_frames(n, w, h, meta["fmt"], meta["depth"], seed=3, kind="natural")
+    for od in ((0, 8) if meta["depth"] == 10 else (0,)):
+        o = Oracle(); program_case(o, G, case)
+        exp = o.add_grain_frames(frames, n, w, h, od)
+        for inplace in ((False, True) if od == 0 else (False,)):
+            hw.reset(); program_case(hw, G, case)
+            got = run_device(hw, frames, n, w, h, od, meta["depth"], inplace=inplace)
+            assert np.array_equal(got, exp), (case, od, inplace, first_mismatch(got, exp, w, h, meta["fmt"], n))
+            assert hw.get_lfsr() == o.get_lfsr()
+
+
 @pytest.mark.parametrize("case,od", [("fgs_sei_ff_test5.cfg|d10|420|g100", 0), ("fgs_afgs1_test1.cfg|d10|420|g100", 8),
                                       ("fgs_sei.cfg|d8|420|g100", 0)])
 def test_host_pipeline_many_chunks(hw, case, od):

@@ -33,6 +33,13 @@ def run_emu(emu, o: Oracle, frames, n, w, h, od, first=0, mode=0):
     return out, mask
 
 
+def run_emu_inplace(emu, o: Oracle, frames, n, w, h, first=0):
+    st = RefState()
+    o.L.oracle_get_state(o.h, C.byref(st))
+    mask = emu.emu_add_grain_frames(C.byref(st), _ptr(frames), _ptr(frames), n, w, h, 0, first, 0)
+    return frames, mask
+
+
 @pytest.mark.parametrize("case", CASES)
 def test_emulated_kernel_equals_oracle(emu, case):
     meta = G.cases[case]
@@ -109,3 +116,30 @@ def test_extreme_geometries(emu, w, h, n):
         want = o.add_grain_frames(frames, n, w, h, 0)
         for mode, (got, _) in runs:
             assert np.array_equal(got, want), (case, w, h, mode, first_mismatch(got, want, w, h, meta["fmt"], n))
+
+
+@pytest.mark.parametrize("case", ["fgs_sei.cfg|d10|420|g100", "fgs_sei.cfg|d8|420|g100", "fgs_sei_ff_test5.cfg|d10|420|g100",
+                                  "fgs_sei_ff_test7.cfg|d10|420|g100"])
+def test_smooth_pictures_take_the_octet_path(emu, case):
+    """Natural-looking frames (smooth gradient + small noise): most lanes see one pattern slot in their eight samples, so
+    the gather task code fetches whole words of a slot row instead of byte gathers; results as ever, and the path is
+    really taken (by most lane-lines, but not by all: the slow side stays covered in the same run)."""
+    meta = G.cases[case]
+    emu.emu_octet_lines.restype = C.c_longlong
+    for (w, h, n) in ((1024, 72, 2), (528, 40, 1)):
+        for od in ((0, 8) if meta["depth"] == 10 else (0,)):
+            frames = synth_frames(n, w, h, meta["fmt"], meta["depth"], seed=3, kind="natural")
+            o = Oracle(); program_case(o, G, case)
+            emu.emu_octet_lines()
+            got, mask = run_emu(emu, o, frames, n, w, h, od)
+            hits = emu.emu_octet_lines()
+            want = o.add_grain_frames(frames, n, w, h, od)
+            assert mask & 4 and np.array_equal(got, want), (case, w, h, od, first_mismatch(got, want, w, h, meta["fmt"], n))
+            gathered = sum(1 for k in (0, 1, 2) if (np.unique(G.state(case)["plut"][k] >> 4).size > 1))  # components on the gather code
+            assert hits > 0 and gathered > 0, "no lane took the octet path"
+            buf = frames.copy()  # in place (shifted unit numbering)
+            emu.emu_add_grain_frames  # noqa: B018
+            if od == 0:
+                st_o = Oracle(); program_case(st_o, G, case)
+                got2, mask2 = run_emu_inplace(emu, st_o, buf, n, w, h)
+                assert np.array_equal(got2, want) or (mask2 & 2), (case, "in place")

@@ -49,6 +49,7 @@ static_assert(kGatherLB >= 2, "both vertical-overlap lines of a block-row must f
 struct EmuWarp {
 	bool record = false;
 	int lane = 0, point = 0;
+	long long octet_lines = 0; // lane-lines that took the uniform-slot octet path (tests/emu: is it really taken?)
 	int table[64][32];
 };
 inline EmuWarp& emu_warp() { static thread_local EmuWarp w; return w; }
@@ -94,36 +95,74 @@ struct GatherLane {
 	smem_addr_t lut;        // this lane's column of the component's private LUT
 	int s_own, s_up;        // block signs (applied by multiplication when !FOLD)
 	int s_nb, s_nb_up;
+	bool word_aligned;      // own and up are multiples of 4: the lane's eight bytes of a slot row are two whole words
 	int pow16;
 	uint32_t lo2, hi2;
 };
 
-// Unfiltered grain (vertical overlap blended in, block sign applied) and scale of the lane's 8 samples.
-template <bool IN16, bool FOLD, bool OVERLAP, int E>
-VFGS_HD void gather_sample(const GatherLane& L, const uint32_t raw[4], int rc, int ru, int wc, int wu, int& scale, int& grain)
+// Unfiltered grain (vertical overlap blended in, block sign applied) of sample E from its LUT entry: one byte gather
+// (two on an overlap line), bank conflicts as the windows and slots fall.
+template <bool FOLD, bool OVERLAP, int E>
+VFGS_HD int gather_sample(const GatherLane& L, uint32_t ent, int rc, int ru, int wc, int wu)
 {
-	const uint32_t ent = lds32(L.lut | (smem_addr_t)index_bits<IN16, E>(raw));
-	scale = (int)(ent & 0xffu);
 	const smem_addr_t off = (smem_addr_t)(ent >> 8) + E;
 	int g = lds_s8(L.own + rc + off);
 	if (OVERLAP) g = (g * wc + lds_s8(L.up + ru + off) * wu + 16) >> 5; // vfgs_hw.c:223-229; wc / wu carry the signs when !FOLD
 	else if (!FOLD) g *= L.s_own;
-	grain = g;
+	return g;
+}
+template <bool FOLD, bool OVERLAP, int E>
+VFGS_HD int octet_sample(const GatherLane& L, uint32_t c0, uint32_t c1, uint32_t u0, uint32_t u1, int wc, int wu)
+{
+	int g = octet_byte<E>(c0, c1);
+	if (OVERLAP) g = (g * wc + octet_byte<E>(u0, u1) * wu + 16) >> 5;
+	else if (!FOLD) g *= L.s_own;
+	return g;
 }
 
-// One line of one lane, up to the exchange: g[] and sc[].
+// One line of one lane, up to the exchange: g[] and sc[]. The eight LUT lookups come first. A lane whose eight samples all
+// select the same pattern slot (the rule on real pictures: the slot changes with the intensity INTERVAL,
+// vfgs_fw.c:598-622, and neighbouring samples mostly share one) and whose window is word aligned reads its eight
+// grain bytes as two consecutive words of that slot's row. The branch is per lane: in a mixed warp the hardware runs
+// both sides one after the other, each with its own lanes only, and a byte gather issued for a handful of lanes
+// hardly conflicts, so the shared-memory wavefronts (the kernel's bound: profiles/r02_gather_v2.md) shrink with every
+// lane that qualifies. Uniformly random samples never qualify and pay five extra instructions per line for the test.
+#ifndef VFGS_GATHER_OCTET_PATH
+#define VFGS_GATHER_OCTET_PATH 1 // build-time knob for experiments
+#endif
 template <bool IN16, bool FOLD, bool OVERLAP>
 VFGS_HD void gather_grain(const GatherLane& L, const uint32_t raw[4], int rc, int ru, int w_cur, int w_up, int g[8], int sc[8])
 {
 	const int wc = FOLD ? w_cur : w_cur * L.s_own, wu = FOLD ? w_up : w_up * L.s_up;
-	gather_sample<IN16, FOLD, OVERLAP, 0>(L, raw, rc, ru, wc, wu, sc[0], g[0]);
-	gather_sample<IN16, FOLD, OVERLAP, 1>(L, raw, rc, ru, wc, wu, sc[1], g[1]);
-	gather_sample<IN16, FOLD, OVERLAP, 2>(L, raw, rc, ru, wc, wu, sc[2], g[2]);
-	gather_sample<IN16, FOLD, OVERLAP, 3>(L, raw, rc, ru, wc, wu, sc[3], g[3]);
-	gather_sample<IN16, FOLD, OVERLAP, 4>(L, raw, rc, ru, wc, wu, sc[4], g[4]);
-	gather_sample<IN16, FOLD, OVERLAP, 5>(L, raw, rc, ru, wc, wu, sc[5], g[5]);
-	gather_sample<IN16, FOLD, OVERLAP, 6>(L, raw, rc, ru, wc, wu, sc[6], g[6]);
-	gather_sample<IN16, FOLD, OVERLAP, 7>(L, raw, rc, ru, wc, wu, sc[7], g[7]);
+	uint32_t ent[8];
+	ent[0] = lds32(L.lut | (smem_addr_t)index_bits<IN16, 0>(raw)); ent[1] = lds32(L.lut | (smem_addr_t)index_bits<IN16, 1>(raw));
+	ent[2] = lds32(L.lut | (smem_addr_t)index_bits<IN16, 2>(raw)); ent[3] = lds32(L.lut | (smem_addr_t)index_bits<IN16, 3>(raw));
+	ent[4] = lds32(L.lut | (smem_addr_t)index_bits<IN16, 4>(raw)); ent[5] = lds32(L.lut | (smem_addr_t)index_bits<IN16, 5>(raw));
+	ent[6] = lds32(L.lut | (smem_addr_t)index_bits<IN16, 6>(raw)); ent[7] = lds32(L.lut | (smem_addr_t)index_bits<IN16, 7>(raw));
+#pragma unroll
+	for (int e = 0; e < 8; e++) sc[e] = (int)(ent[e] & 0xffu);
+	if (VFGS_GATHER_OCTET_PATH) {
+		const uint32_t diff = ((ent[0] ^ ent[1]) | (ent[0] ^ ent[2]) | (ent[0] ^ ent[3])) | ((ent[0] ^ ent[4]) | (ent[0] ^ ent[5]) | (ent[0] ^ ent[6])) |
+		                      (ent[0] ^ ent[7]);
+		if ((diff >> 8) == 0 && L.word_aligned) {
+#if !defined(__CUDA_ARCH__)
+			emu_warp().octet_lines++;
+#endif
+			const smem_addr_t a = L.own + rc + (smem_addr_t)(ent[0] >> 8);
+			const uint32_t c0 = lds32(a), c1 = lds32(a + 4);
+			uint32_t u0 = 0, u1 = 0;
+			if (OVERLAP) { const smem_addr_t b = L.up + ru + (smem_addr_t)(ent[0] >> 8); u0 = lds32(b); u1 = lds32(b + 4); }
+			g[0] = octet_sample<FOLD, OVERLAP, 0>(L, c0, c1, u0, u1, wc, wu); g[1] = octet_sample<FOLD, OVERLAP, 1>(L, c0, c1, u0, u1, wc, wu);
+			g[2] = octet_sample<FOLD, OVERLAP, 2>(L, c0, c1, u0, u1, wc, wu); g[3] = octet_sample<FOLD, OVERLAP, 3>(L, c0, c1, u0, u1, wc, wu);
+			g[4] = octet_sample<FOLD, OVERLAP, 4>(L, c0, c1, u0, u1, wc, wu); g[5] = octet_sample<FOLD, OVERLAP, 5>(L, c0, c1, u0, u1, wc, wu);
+			g[6] = octet_sample<FOLD, OVERLAP, 6>(L, c0, c1, u0, u1, wc, wu); g[7] = octet_sample<FOLD, OVERLAP, 7>(L, c0, c1, u0, u1, wc, wu);
+			return;
+		}
+	}
+	g[0] = gather_sample<FOLD, OVERLAP, 0>(L, ent[0], rc, ru, wc, wu); g[1] = gather_sample<FOLD, OVERLAP, 1>(L, ent[1], rc, ru, wc, wu);
+	g[2] = gather_sample<FOLD, OVERLAP, 2>(L, ent[2], rc, ru, wc, wu); g[3] = gather_sample<FOLD, OVERLAP, 3>(L, ent[3], rc, ru, wc, wu);
+	g[4] = gather_sample<FOLD, OVERLAP, 4>(L, ent[4], rc, ru, wc, wu); g[5] = gather_sample<FOLD, OVERLAP, 5>(L, ent[5], rc, ru, wc, wu);
+	g[6] = gather_sample<FOLD, OVERLAP, 6>(L, ent[6], rc, ru, wc, wu); g[7] = gather_sample<FOLD, OVERLAP, 7>(L, ent[7], rc, ru, wc, wu);
 }
 
 // Unfiltered grain of the sample `v` next to a warp's end lane, from that sample's own intensity and its own block's
@@ -296,6 +335,7 @@ VFGS_HD void gather_task_body(const FgsParams& p, smem_addr_t luts, smem_addr_t 
 	L.up = L.nb = L.nb_up = L.own; L.s_up = L.s_nb = L.s_nb_up = 1;
 	const bool ovl = valid && r > 0; // the first lines of a stripe overlap the block-row above (never in the first stripe, y <= 15)
 	if (ovl) L.up = gather_window<FOLD>(bank_addr, neg_off, (w_cur - p.spitch * 4)[0], i0, L.s_up);
+	L.word_aligned = ((L.own | L.up) & 3) == 0; // pattern rows and slots are multiples of 4 bytes apart (vfgs_tables.h)
 	if (!SHIFT && mem_halo) { // the neighbouring block's window: its last column (left neighbour) or its first (right neighbour)
 		const int nbo = mem_right ? 4 : -4, col = mem_right ? 0 : n - 1;
 		L.nb = gather_window<FOLD>(bank_addr, neg_off, w_cur[nbo], col, L.s_nb);

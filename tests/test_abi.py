@@ -17,7 +17,7 @@ G = load_golden()
 
 def declared_functions():
     names = []
-    for hdr in ("vfgs_hw.h", "vfgs_b200.h"):
+    for hdr in ("vfgs_hw.h", "vfgs_b200.h", "vfgs_fw.h"):
         text = open(os.path.join(ROOT, "include", hdr)).read()
         text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
         names += re.findall(r"\b(vfgs_[a-z0-9_]+)\s*\(", text)

@@ -27,7 +27,7 @@ B200_SYMBOLS = (
     "vfgs_b200_add_grain_frames_host", "vfgs_b200_skip_frames", "vfgs_b200_get_lfsr",
     "vfgs_b200_set_lfsr", "vfgs_b200_host_alloc", "vfgs_b200_host_free", "vfgs_b200_launch_count",
     "vfgs_b200_last_launch", "vfgs_b200_get_state", "vfgs_b200_kernel_timing", "vfgs_b200_kernel_time",
-    "vfgs_b200_force_general_kernel", "vfgs_b200_pipeline_stats",
+    "vfgs_b200_force_general_kernel", "vfgs_b200_pipeline_stats", "vfgs_b200_init_sei", "vfgs_b200_init_afgs1",
 )
 
 
@@ -91,6 +91,8 @@ def load_library(global_symbols: bool = False) -> C.CDLL:
     L.vfgs_b200_kernel_time.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     L.vfgs_b200_force_general_kernel.argtypes = [ci]
     L.vfgs_b200_force_general_kernel.restype = None
+    L.vfgs_b200_init_sei.argtypes = [vp]
+    L.vfgs_b200_init_afgs1.argtypes = [vp]
     L.vfgs_b200_get_state.argtypes = [vp, C.c_size_t]
     L.vfgs_b200_get_state.restype = C.c_size_t
     _lib = L
@@ -129,6 +131,17 @@ class VfgsHw:
     def vfgs_add_grain_line(self, Y, U, V, y, width):
         """One picture line of host memory (numpy arrays), in place."""
         self.L.vfgs_add_grain_line(_np_ptr(Y), _np_ptr(U), _np_ptr(V), y, width)
+
+    # ---- vfgs_fw.h: the firmware layer with the pattern synthesis on the device ---------------
+    def init_sei(self, raw: bytes):
+        """raw: the bytes of an fgs_sei struct (src/vfgs_fw.h:53-62)."""
+        buf = (C.c_uint8 * len(raw)).from_buffer_copy(raw)
+        self._chk(self.L.vfgs_b200_init_sei(buf))
+
+    def init_afgs1(self, raw: bytes):
+        """raw: the bytes of an fgs_afgs1 struct (src/vfgs_fw.h:64-91)."""
+        buf = (C.c_uint8 * len(raw)).from_buffer_copy(raw)
+        self._chk(self.L.vfgs_b200_init_afgs1(buf))
 
     # ---- vfgs_b200.h ------------------------------------------------------------------------
     def reset(self): self._chk(self.L.vfgs_b200_reset())

@@ -17,8 +17,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvfgs_b200.so")
 SOURCES = [os.path.join(CSRC, "vfgs_b200.cu")]
 HEADERS = [os.path.join(CSRC, n) for n in ("vfgs_core.h", "fgs_task.h", "fgs_fast.h", "fgs_gather.h", "vfgs_tables.h",
-                                            "vfgs_kernels.cuh", "yuv_pipeline.h")] + [
-    os.path.join(os.path.dirname(HERE), "include", n) for n in ("vfgs_hw.h", "vfgs_b200.h", "yuv.h")]
+                                            "vfgs_kernels.cuh", "yuv_pipeline.h", "fw_device.h", "fw_host.h", "h274_tables.h")] + [
+    os.path.join(os.path.dirname(HERE), "include", n) for n in ("vfgs_hw.h", "vfgs_b200.h", "yuv.h", "vfgs_fw.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

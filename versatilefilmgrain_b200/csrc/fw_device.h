@@ -120,12 +120,12 @@ VFGS_HD void fw_ff_phase3(const FwJob& j, const FwTables& t, FwScratch& s, int t
 
 // ---- auto-regressive pattern ------------------------------------------------------------------
 // phase 0 (one thread): the causal filter in raster order, vfgs_fw.c:465-495
-VFGS_HD void fw_ar_phase0(const FwJob& j, const FwTables& t, FwScratch& s)
+// buf: the field being generated (82 x 73 or 44 x 38 bytes; shared memory on the device), buf0: the luma field,
+// gauss: the Gaussian table
+VFGS_HD void fw_ar_phase0(const FwJob& j, const int8_t* gauss, int8_t* buf, const int8_t* buf0)
 {
 	const int sub = j.size == 32 ? 2 : 1;
 	const int width = sub > 1 ? 44 : 82, height = sub > 1 ? 38 : 73;
-	int8_t* buf = j.size == 32 ? s.Cbuf : s.Lbuf;
-	const int8_t* buf0 = s.Lbuf;
 	uint32_t rnd = j.seed;
 	for (int y = 0; y < height; y++)
 		for (int x = 0; x < width; x++) {
@@ -143,7 +143,7 @@ VFGS_HD void fw_ar_phase0(const FwJob& j, const FwTables& t, FwScratch& s)
 				}
 				g = fw_round(g, j.scale);
 			}
-			g += fw_round((int)t.gauss[rnd & 2047], j.shift);
+			g += fw_round((int)gauss[rnd & 2047], j.shift);
 			rnd = lfsr_step(rnd);
 			buf[width * y + x] = (int8_t)(g > 127 ? 127 : g < -127 ? -127 : g);
 		}
@@ -177,7 +177,7 @@ VFGS_HD void fw_store_phase(const FwJob& j, const FwScratch& s, int8_t* pattern 
 // Whole job with one thread (host build).
 inline void fw_run_job_serial(const FwJob& j, const FwTables& t, FwScratch& s, int8_t* pattern)
 {
-	if (j.kind == kFwAR) { fw_ar_phase0(j, t, s); fw_ar_phase1(j, s, 0, 1); }
+	if (j.kind == kFwAR) { fw_ar_phase0(j, t.gauss, j.size == 32 ? s.Cbuf : s.Lbuf, s.Lbuf); fw_ar_phase1(j, s, 0, 1); }
 	else { fw_ff_phase0(j, s); fw_ff_phase1(j, t, s, 0, 1); fw_ff_phase2(j, t, s, 0, 1); fw_ff_phase3(j, t, s, 0, 1); }
 	fw_store_phase(j, s, pattern, 0, 1);
 }

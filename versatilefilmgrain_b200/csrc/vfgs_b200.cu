@@ -13,9 +13,11 @@
 #include <vector>
 
 #include "../../include/vfgs_b200.h"
+#include "../../include/vfgs_fw.h"
 #include "../../include/vfgs_hw.h"
 #include "../../include/yuv.h"
 #include "vfgs_kernels.cuh"
+#include "fw_host.h"
 
 using namespace vfgs;
 
@@ -30,6 +32,15 @@ struct Slot { // one stage of the host pipeline
 	cudaEvent_t h2d_done = nullptr, k_done = nullptr, d2h_done = nullptr;
 };
 constexpr int kPipeSlots = 4;
+constexpr int kImageSets = 4;
+constexpr size_t kImageBlobCap = 192u << 10, kImageFblobCap = 128u << 10; // upper bounds of build_tables' images
+struct ImageSet {
+	uint8_t* d_blob = nullptr;   // general image (+ negated slot copies)
+	uint8_t* d_fblob = nullptr;  // fast-path image
+	uint8_t* h_stage = nullptr;  // page-locked staging of both, the source of the asynchronous upload
+	cudaEvent_t uploaded = nullptr, last_use = nullptr;
+	bool in_use = false;
+};
 constexpr size_t kBlockTableBytes = sizeof(uint32_t) + 4 * sizeof(uint16_t); // per block: LFSR register + window offsets
 
 struct Context {
@@ -39,10 +50,16 @@ struct Context {
 	int max_smem_optin = 0;
 	int fast_pad = 0;           // gap between the fast kernel's dynamic shared memory and the next 32 KB boundary (measured by a probe launch)
 	uint32_t* d_pow2 = nullptr;
-	uint8_t* d_blob = nullptr;
-	size_t blob_cap = 0;
-	uint8_t* d_fblob = nullptr; // fast-path table image
-	size_t fblob_cap = 0;
+	// Table images (general + fast, vfgs_tables.h) live in a small ring of sets: a configuration change builds the next
+	// set and uploads it asynchronously on the table stream, while frames already queued keep reading the set they were
+	// launched with. A set is reused kImageSets changes later, after the last kernel that read it (last_use) is done.
+	ImageSet img[kImageSets];
+	int img_cur = -1;
+	// firmware layer on the device (vfgs_b200_init_sei / _afgs1): constant tables, working memory, pattern store, staging
+	FwTables* d_fw_tables = nullptr;
+	FwScratch* d_fw_scratch = nullptr;
+	int8_t* d_fw_pattern = nullptr;
+	int8_t* h_fw_stage = nullptr;
 	int fast_smem_attr = 0, gather_smem_attr = 0;
 	uint32_t* d_streams = nullptr; // device entry point / line path
 	size_t streams_cap = 0;
@@ -165,6 +182,13 @@ int ensure_ctx(int device)
 		CUDA_TRY(cudaEventCreateWithFlags(&c.tab_ready[t], cudaEventDisableTiming));
 		CUDA_TRY(cudaEventCreateWithFlags(&c.tab_free[t], cudaEventDisableTiming));
 	}
+	for (ImageSet& m : c.img) { // fixed-size allocations: nothing is (re)allocated, hence nothing synchronises, on a configuration change
+		CUDA_TRY(cudaMalloc((void**)&m.d_blob, kImageBlobCap));
+		CUDA_TRY(cudaMalloc((void**)&m.d_fblob, kImageFblobCap));
+		CUDA_TRY(cudaHostAlloc((void**)&m.h_stage, kImageBlobCap + kImageFblobCap, cudaHostAllocDefault));
+		CUDA_TRY(cudaEventCreateWithFlags(&m.uploaded, cudaEventDisableTiming));
+		CUDA_TRY(cudaEventCreateWithFlags(&m.last_use, cudaEventDisableTiming));
+	}
 	for (Slot& s : c.slot) {
 		CUDA_TRY(cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
 		CUDA_TRY(cudaEventCreateWithFlags(&s.k_done, cudaEventDisableTiming));
@@ -197,17 +221,41 @@ int upload_blob()
 	build_blob();
 	if (g_bi.bytes > c.max_smem_optin - 1024)
 		return set_err(VFGS_B200_ERR_STATE, "table image of %d bytes exceeds shared memory", g_bi.bytes);
-	// frames still in flight read the old image: drain before overwriting (config changes are rare)
-	CUDA_TRY(cudaDeviceSynchronize());
-	if (int rc = grow(c.d_blob, c.blob_cap, (size_t)g_bi.gbytes)) return rc;
-	CUDA_TRY(cudaMemcpy(c.d_blob, g_blob.data(), (size_t)g_bi.gbytes, cudaMemcpyHostToDevice));
+	if ((size_t)g_bi.gbytes > kImageBlobCap || (size_t)g_bi.fbytes > kImageFblobCap)
+		return set_err(VFGS_B200_ERR_STATE, "table images of %d + %d bytes exceed their buffers", g_bi.gbytes, g_bi.fbytes);
+	// next set of the ring; frames in flight keep reading theirs. Only if the set is still being read by kernels
+	// launched kImageSets configuration changes ago does the host wait, and then for those kernels alone.
+	const int next = (c.img_cur + 1) % kImageSets;
+	ImageSet& m = c.img[next];
+	if (m.in_use) CUDA_TRY(cudaEventSynchronize(m.last_use));
+	memcpy(m.h_stage, g_blob.data(), (size_t)g_bi.gbytes);
+	memcpy(m.h_stage + kImageBlobCap, g_fblob.data(), (size_t)g_bi.fbytes);
+	CUDA_TRY(cudaMemcpyAsync(m.d_blob, m.h_stage, (size_t)g_bi.gbytes, cudaMemcpyHostToDevice, c.s_tab));
+	CUDA_TRY(cudaMemcpyAsync(m.d_fblob, m.h_stage + kImageBlobCap, (size_t)g_bi.fbytes, cudaMemcpyHostToDevice, c.s_tab));
+	CUDA_TRY(cudaEventRecord(m.uploaded, c.s_tab));
+	m.in_use = false;
+	c.img_cur = next;
 	if (g_bi.bytes > c.smem_attr) {
 		CUDA_TRY(cudaFuncSetAttribute(fgs_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_bi.bytes));
 		c.smem_attr = g_bi.bytes;
 	}
-	if (int rc = grow(c.d_fblob, c.fblob_cap, (size_t)g_bi.fbytes)) return rc;
-	CUDA_TRY(cudaMemcpy(c.d_fblob, g_fblob.data(), (size_t)g_bi.fbytes, cudaMemcpyHostToDevice));
 	g_dirty = false;
+	return VFGS_B200_OK;
+}
+
+// Grain kernels about to be launched on `stream` read the current image set: they wait for its upload, and the set
+// remembers the last stream position that reads it.
+int images_before(cudaStream_t stream)
+{
+	ImageSet& m = g_ctx.img[g_ctx.img_cur];
+	CUDA_TRY(cudaStreamWaitEvent(stream, m.uploaded, 0));
+	return VFGS_B200_OK;
+}
+int images_after(cudaStream_t stream)
+{
+	ImageSet& m = g_ctx.img[g_ctx.img_cur];
+	CUDA_TRY(cudaEventRecord(m.last_use, stream));
+	m.in_use = true;
 	return VFGS_B200_OK;
 }
 
@@ -253,7 +301,8 @@ void fill_common(FgsParams& p, const Geometry& g)
 	fill_state_params(p, hw(), g_bi);
 	p.nb = g.nb; p.R = g.R;
 	p.in_bytes = (int)g.in_sample; p.out_bytes = (int)g.out_sample;
-	p.blob = g_ctx.d_blob; p.fblob = g_ctx.d_fblob;
+	p.blob = g_ctx.img_cur >= 0 ? g_ctx.img[g_ctx.img_cur].d_blob : nullptr;
+	p.fblob = g_ctx.img_cur >= 0 ? g_ctx.img[g_ctx.img_cur].d_fblob : nullptr;
 	p.spitch = g.spitch;
 }
 
@@ -411,13 +460,14 @@ int run_frames_device(const vfgs_b200_planes& in, const vfgs_b200_planes& out, i
 		CUDA_TRY(cudaEventRecord(table_ready, table_stream));
 		CUDA_TRY(cudaStreamWaitEvent(stream, table_ready, 0));
 	}
+	if (int rc = images_before(stream)) return rc;
 	if (lp.any_fast)
 		if (int rc = launch_apply(lp.fast, stream, kFast)) return rc;
 	if (lp.any_gather)
 		if (int rc = launch_apply(lp.gather, stream, kGather, lp.gather_smem, lp.gather_fold, lp.gather_shift)) return rc;
 	if (lp.any_general)
 		if (int rc = launch_apply(lp.general, stream, kGeneral)) return rc;
-	return VFGS_B200_OK;
+	return images_after(stream);
 }
 
 // How the output planes lie relative to the input planes: 0 disjoint, 1 in place (every overlapping plane pair is
@@ -635,7 +685,7 @@ void vfgs_add_grain_line(void* Y, void* U, void* V, int y, int width)
 	}
 	p.states = c.d_streams; p.stream_rows = 2; p.stream_row0 = (y >> 4) - 1;
 	finish_tasks(p);
-	if (launch_apply(p, st)) fatal("vfgs_add_grain_line");
+	if (images_before(st) || launch_apply(p, st) || images_after(st)) fatal("vfgs_add_grain_line");
 	chk(cudaMemcpyAsync(Y, c.d_line + region, lbytes, cudaMemcpyDeviceToHost, st), "Y D2H");
 	if (chroma) {
 		chk(cudaMemcpyAsync(U, c.d_line + region + lpad, cbytes, cudaMemcpyDeviceToHost, st), "U D2H");
@@ -888,6 +938,88 @@ int vfgs_b200_kernel_time(double* total_ms, uint64_t* launches)
 void vfgs_b200_last_launch(int out[5])
 {
 	for (int i = 0; i < 5; i++) out[i] = g_ctx.last_launch[i];
+}
+
+} // extern "C"
+
+// ====================================================================================== vfgs_fw.h
+namespace {
+
+int ensure_fw()
+{
+	Context& c = g_ctx;
+	if (c.d_fw_tables) return VFGS_B200_OK;
+	static FwTables tables;
+	make_fw_tables(tables);
+	CUDA_TRY(cudaMalloc((void**)&c.d_fw_tables, sizeof(FwTables)));
+	CUDA_TRY(cudaMemcpy(c.d_fw_tables, &tables, sizeof(FwTables), cudaMemcpyHostToDevice));
+	CUDA_TRY(cudaMalloc((void**)&c.d_fw_scratch, sizeof(FwScratch)));
+	CUDA_TRY(cudaMemset(c.d_fw_scratch, 0, sizeof(FwScratch)));
+	CUDA_TRY(cudaMalloc((void**)&c.d_fw_pattern, 2 * kSlots * 4096));
+	CUDA_TRY(cudaMemset(c.d_fw_pattern, 0, 2 * kSlots * 4096));
+	CUDA_TRY(cudaHostAlloc((void**)&c.h_fw_stage, 2 * kFwMaxPatterns * 4096, cudaHostAllocDefault));
+	return VFGS_B200_OK;
+}
+
+// Pattern jobs on the table stream, results into the host mirror through the setters' copy rules, then LUTs and
+// scalars through the setters themselves. The host waits for the job kernels only (tens of microseconds each; the
+// auto-regressive filter is serial: ~0.2 ms): grain kernels queued on other streams keep running.
+int fw_apply(FwPlan& plan)
+{
+	if (plan.error) return set_err(VFGS_B200_ERR_STATE, "%s", plan.error);
+	if ((int)plan.jobs.size() > 2 * kFwMaxPatterns) return set_err(VFGS_B200_ERR_STATE, "too many patterns");
+	pipe_before_state_change();
+	if (int rc = ensure_ctx(-1)) return rc;
+	if (int rc = ensure_fw()) return rc;
+	Context& c = g_ctx;
+	HwState& h = hw();
+	for (size_t i = 0; i < plan.jobs.size(); i++) {
+		const FwJob& j = plan.jobs[i];
+		fw_pattern_kernel<<<1, kFwThreads, 0, c.s_tab>>>(j, c.d_fw_tables, c.d_fw_scratch, c.d_fw_pattern);
+		CUDA_TRY(cudaGetLastError());
+		g_launches++;
+		CUDA_TRY(cudaMemcpyAsync(c.h_fw_stage + i * 4096, c.d_fw_pattern + ((size_t)j.bank * kSlots + j.slot) * 4096, 4096,
+		                         cudaMemcpyDeviceToHost, c.s_tab));
+	}
+	CUDA_TRY(cudaStreamSynchronize(c.s_tab));
+	for (size_t i = 0; i < plan.jobs.size(); i++) {
+		const FwJob& j = plan.jobs[i];
+		const int8_t* src = c.h_fw_stage + i * 4096;
+		if (j.bank == 0) memcpy(h.pattern[0][j.slot], src, 4096);                 // vfgs_set_luma_pattern
+		else                                                                     // vfgs_set_chroma_pattern: only the rows and columns it writes
+			for (int r = 0; r < 64 / h.csuby; r++) memcpy(h.pattern[1][j.slot][r], src + 64 * r, (size_t)(64 / h.csubx));
+	}
+	g_dirty = true;
+	if (plan.set_seed) vfgs_set_seed(plan.seed);
+	for (int cc = 0; cc < 3; cc++) {
+		vfgs_set_scale_lut(cc, plan.slut[cc]);
+		vfgs_set_pattern_lut(cc, plan.plut[cc]);
+	}
+	if (plan.scale_shift < 2 || plan.scale_shift >= 8)
+		return set_err(VFGS_B200_ERR_STATE, "scale shift %d outside 2..7 (the reference asserts, vfgs_hw.c:348)", plan.scale_shift);
+	vfgs_set_scale_shift(plan.scale_shift);
+	if (plan.set_legal) vfgs_set_legal_range(plan.legal);
+	return VFGS_B200_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int vfgs_b200_init_sei(const fgs_sei* cfg) // vfgs_fw.c:517-644
+{
+	if (!cfg) return set_err(VFGS_B200_ERR_ARG, "null metadata");
+	FwPlan plan;
+	fw_plan_sei(*cfg, hw().csubx, hw().csuby, plan);
+	return fw_apply(plan);
+}
+
+int vfgs_b200_init_afgs1(const fgs_afgs1* cfg) // vfgs_fw.c:663-708
+{
+	if (!cfg) return set_err(VFGS_B200_ERR_ARG, "null metadata");
+	FwPlan plan;
+	fw_plan_afgs1(*cfg, hw().csubx, hw().csuby, plan);
+	return fw_apply(plan);
 }
 
 } // extern "C"

@@ -13,6 +13,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "vfgs_tables.h"
+#include "fw_device.h"
 
 namespace vfgs {
 
@@ -236,6 +237,40 @@ fgs_apply_gather_kernel(const __grid_constant__ FgsParams p)
 	const long long stride = (long long)gridDim.x * kGatherWarps;
 	for (long long task = (long long)blockIdx.x * kGatherWarps + (threadIdx.x >> 5); task < p.total_tasks; task += stride)
 		process_task_gather<IN16, OUT8, FOLD, SHIFT>(p, luts, img, (uint32_t)task, lane);
+}
+
+// ---- firmware layer: one pattern job (fw_device.h) -----------------------------------------------
+// One CTA per job, jobs of a configuration one after the other on the table stream (they share the firmware's pattern
+// buffer, fw_device.h). The frequency-filtering job is two 64 x 64 x 64 integer matrix passes spread over the CTA; the
+// auto-regressive filter is causal in raster order: one thread walks it in shared memory (6,000 samples x <= 24 taps).
+constexpr int kFwThreads = 256;
+__global__ void __launch_bounds__(kFwThreads)
+fw_pattern_kernel(const FwJob job, const FwTables* __restrict__ tables, FwScratch* scratch, int8_t* pattern)
+{
+	__shared__ int8_t field[73 * 82];
+	__shared__ int8_t gauss[2048];
+	const int tid = threadIdx.x;
+	if (job.kind == kFwAR) {
+		const int sub = job.size == 32 ? 2 : 1, bytes = sub > 1 ? 44 * 38 : 82 * 73;
+		for (int i = tid; i < 2048; i += kFwThreads) gauss[i] = tables->gauss[i];
+		__syncthreads();
+		if (tid == 0) fw_ar_phase0(job, gauss, field, scratch->Lbuf);
+		__syncthreads();
+		int8_t* keep = sub > 1 ? scratch->Cbuf : scratch->Lbuf; // the luma field stays for the chroma jobs (luma injection)
+		for (int i = tid; i < bytes; i += kFwThreads) keep[i] = field[i];
+		__syncthreads();
+		fw_ar_phase1(job, *scratch, tid, kFwThreads);
+	} else {
+		if (tid == 0) fw_ff_phase0(job, *scratch);
+		__syncthreads();
+		fw_ff_phase1(job, *tables, *scratch, tid, kFwThreads);
+		__syncthreads();
+		fw_ff_phase2(job, *tables, *scratch, tid, kFwThreads);
+		__syncthreads();
+		fw_ff_phase3(job, *tables, *scratch, tid, kFwThreads);
+	}
+	__syncthreads();
+	fw_store_phase(job, *scratch, pattern, tid, kFwThreads);
 }
 
 } // namespace vfgs

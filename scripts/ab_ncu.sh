@@ -10,7 +10,7 @@ cp $LIB /tmp/keep.so
 for so in ${LIBS:-build/ab/libs/*.so}; do
   n=$(basename $so .so)
   cp $so $LIB; touch $LIB
-  CMD="python bench.py --steps 2 --warmup 3 --frames-per-step 64 --passes 1 --e2e-frames 4 --no-cpu-baseline --skip-parity-gate --workload $WL"
+  CMD="python bench.py --steps 2 --warmup 3 --frames-per-step 64 --passes 1 --e2e-frames 4 --no-cpu-baseline --no-sustained-copy --skip-parity-gate --workload $WL"
   timeout 900 ncu --set full --clock-control none ${NCU_EXTRA:-} --import-source on -k regex:fgs_apply -s 3 -c 1 -f -o gpurun_out/ab_${n}_${WL}${TAG:-} $CMD > gpurun_out/ab_ncu_$n.log 2>&1
   echo "$n ncu rc=$?"
 done

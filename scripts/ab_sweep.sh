@@ -15,9 +15,10 @@ done
 for r in $(seq 1 ${ROUNDS:-2}); do
   for so in build/ab/libs/*.so; do
     n=$(basename $so .so)
+    if [ -n "${ONLY:-}" ] && ! [[ "$n" =~ $ONLY ]]; then continue; fi
     cp $so $LIB; touch $LIB
     for wl in $WLS; do
-      python bench.py --no-cpu-baseline --skip-parity-gate --steps ${STEPS:-20} --warmup 5 --e2e-frames 8 --workload $wl ${EXTRA:-} 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$n', d['config']['name'], round(d['value']), 'fps', round(d['roofline']['achieved']), 'GB/s', round(d['roofline']['frac'],3))"
+      python bench.py --no-cpu-baseline --no-sustained-copy --skip-parity-gate --steps ${STEPS:-20} --warmup 5 --e2e-frames 8 --workload $wl ${EXTRA:-} 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$n', d['config']['name'], round(d['value']), 'fps', round(d['roofline']['achieved']), 'GB/s', round(d['roofline']['frac'],3))"
     done
   done
 done

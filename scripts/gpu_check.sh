@@ -25,7 +25,7 @@ for wl in ${WORKLOADS:-}; do
 done
 
 if [ "${NCU:-1}" = "1" ]; then
-  CMD="python bench.py --steps 2 --warmup 3 --frames-per-step 64 --passes 1 --e2e-frames 4 --no-cpu-baseline --skip-parity-gate --workload ${NCU_WL:-4k420_afgs1_10to10}"
+  CMD="python bench.py --steps 2 --warmup 3 --frames-per-step 64 --passes 1 --e2e-frames 4 --no-cpu-baseline --no-sustained-copy --skip-parity-gate --workload ${NCU_WL:-4k420_afgs1_10to10}"
   timeout 600 $CMD > gpurun_out/ncu_plain.log 2>&1 &&
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
       --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1

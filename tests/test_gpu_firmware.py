@@ -42,7 +42,7 @@ def test_device_firmware_programs_the_reference_state(hw, case):
 
 
 @pytest.mark.parametrize("case", ["fgs_sei.cfg|d10|420|g100", "fgs_sei_ar_test1.cfg|d10|420|g100", "fgs_afgs1_test1.cfg|d10|420|g100",
-                                  "fgs_sei_ff_test5.cfg|d8|420|g100"])
+                                  "fgs_sei_ff_test7.cfg|d8|420|g100"])
 def test_device_firmware_then_frames(hw, case):
     import torch
     meta = G.cases[case]

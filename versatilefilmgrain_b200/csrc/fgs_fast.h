@@ -184,6 +184,16 @@ VFGS_HD void ld_samples_16_if(const uint8_t* p, uint32_t r[4], bool pred)
 #endif
 }
 
+// line prefetch into L1 (no destination register), only when pred is set
+VFGS_HD void prefetch_l1(const uint8_t* p, bool pred)
+{
+#if defined(__CUDA_ARCH__)
+	asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %1, 0;\n\t@q prefetch.global.L1 [%0];\n\t}" :: "l"(p), "r"((uint32_t)pred));
+#else
+	(void)p; (void)pred;
+#endif
+}
+
 // global load that only happens when pred is set; the destination keeps its value otherwise
 VFGS_HD void ld_global_16_if(const uint8_t* p, uint32_t r[4], bool pred)
 {
@@ -386,6 +396,12 @@ VFGS_HD uint32_t window_offset(uint32_t s, const WoffComp& w)
 #define VFGS_FAST_LB 4
 #endif
 constexpr int kFastLB = VFGS_FAST_LB; // lines in flight per lane (build-time knob for experiments)
+#ifndef VFGS_FAST_PREFETCH16
+#define VFGS_FAST_PREFETCH16 0 // lines ahead of the line loads prefetched into L1, 16-bit output (build-time knob for experiments)
+#endif
+#ifndef VFGS_FAST_PREFETCH8
+#define VFGS_FAST_PREFETCH8 0  // same, 8-bit output
+#endif
 static_assert(kFastLB >= 2, "both vertical-overlap lines of a block-row must fall into the first group of lines");
 #ifndef VFGS_FAST_LB16
 #define VFGS_FAST_LB16 VFGS_FAST_LB // fast kernel, 16-bit (or 8-bit in, 8-bit out) stores
@@ -413,7 +429,8 @@ VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, const TaskGeom&
 	if (nl <= 0) return;
 
 	constexpr int IB = IN16 ? 2 : 1, OB = (IN16 && !OUT8) ? 2 : 1;
-	constexpr bool kL1 = VFGS_FAST_L1_MODE == 2 || (VFGS_FAST_L1_MODE == 1 && !OUT8); // sample loads allocate in L1
+	constexpr int PF = OUT8 ? VFGS_FAST_PREFETCH8 : VFGS_FAST_PREFETCH16;            // lines prefetched ahead of the line loads
+	constexpr bool kL1 = VFGS_FAST_L1_MODE == 2 || (VFGS_FAST_L1_MODE == 1 && !OUT8) || PF > 0; // sample loads allocate in L1
 	const long long in_pitch = pl.in_row_bytes, out_pitch = pl.out_row_bytes;
 	const uint8_t* src = pl.in + (long long)t.f * p.in_frame_bytes + (long long)cl0 * in_pitch + (long long)k0 * IB;
 	uint8_t* dst = pl.out + (long long)t.f * p.out_frame_bytes + (long long)cl0 * out_pitch + (long long)k0 * OB;
@@ -426,6 +443,11 @@ VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, const TaskGeom&
 		const int qq = q < nl ? q : nl - 1;
 		if (IN16) ld_samples_16<kL1>(src + qq * in_pitch, raw[q]);
 		else ld_global_8(src + qq * in_pitch, raw[q]);
+	}
+
+	if (IN16 && PF > 0) {
+#pragma unroll
+		for (int q = LB; q < LB + PF; q++) prefetch_l1(src + q * in_pitch, q < nl);
 	}
 
 	const int b = k0 >> NSH;
@@ -477,6 +499,7 @@ VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, const TaskGeom&
 				const bool refill = WHOLE ? more : line + LB < nl;
 				if (IN16) ld_samples_16_if<kL1>(nxt, raw[q], refill);
 				else ld_global_8_if(nxt, raw[q], refill);
+				if (IN16 && PF > 0) prefetch_l1(nxt + PF * in_pitch, line + LB + PF < nl);
 				if (WHOLE || line < nl) {
 					if (OB == 2) st_global_16(dst, w);
 					else st_global_8(dst, w);

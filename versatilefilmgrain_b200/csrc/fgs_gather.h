@@ -244,18 +244,37 @@ VFGS_HD uint32_t ld_sample_if(const uint8_t* p, bool pred)
 	return IB == 2 ? (uint32_t)*(const uint16_t*)p : (uint32_t)*p;
 #endif
 }
+// The kernel keeps few lines in flight per lane (registers: LB = 2 at 28 warps = 28 KB per SM) and was bound by the
+// latency of its line loads once the instruction count had come down (long_scoreboard 4.9 warps per issue cycle,
+// profiles/r02_gather_v2.md). Lines further down the stripe are therefore prefetched into L1 (no registers), and the line
+// loads are ordinary cached loads that find them there. Measured on B200 (profiles/r02_gather_ab.md, same box):
+// natural data 0.753 -> 0.835 of the HBM peak, uniform 0.742 -> 0.775 with 4 lines of prefetch.
 #ifndef VFGS_GATHER_PREFETCH
-#define VFGS_GATHER_PREFETCH 0 // lines ahead of the line loads that are prefetched into L1 (build-time knob for experiments)
+#define VFGS_GATHER_PREFETCH 4 // lines ahead of the line loads that are prefetched into L1 (0: none, line loads bypass L1)
 #endif
-VFGS_HD void prefetch_l1(const uint8_t* p, bool pred)
+#ifndef VFGS_GATHER_XPREFETCH
+#define VFGS_GATHER_XPREFETCH 0 // lines of the warp's NEXT task prefetched while the current one ends (build-time knob for experiments)
+#endif
+// line loads of the gather kernel: cached (they hit the prefetched lines) unless prefetching is off
+template <bool IN16>
+VFGS_HD void gather_ld_if(const uint8_t* p, uint32_t r[4], bool pred)
 {
+	if (VFGS_GATHER_PREFETCH > 0) {
 #if defined(__CUDA_ARCH__)
-	asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %1, 0;\n\t@q prefetch.global.L1 [%0];\n\t}" :: "l"(p), "r"((uint32_t)pred));
+		if (IN16)
+			asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q ld.global.v4.u32 {%0,%1,%2,%3}, [%4];\n\t}"
+			             : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]) : "l"(p), "r"((uint32_t)pred));
+		else
+			asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q ld.global.v2.u32 {%0,%1}, [%2];\n\t}"
+			             : "+r"(r[0]), "+r"(r[1]) : "l"(p), "r"((uint32_t)pred));
 #else
-	(void)p; (void)pred;
+		if (pred) memcpy(r, p, IN16 ? 16 : 8);
 #endif
+	} else {
+		if (IN16) ld_global_16_if(p, r, pred);
+		else ld_global_8_if(p, r, pred);
+	}
 }
-
 // One warp-task: 32 consecutive flat lane units of a component (lane = 8 samples: half a 16-sample block with one
 // block edge, NSH = 4, or a whole 8-sample block with an edge at both ends, NSH = 3). Units run over all stripes of
 // a frame; rows are padded to an even number of units so that the parity of a unit is the parity of its lane.
@@ -263,7 +282,7 @@ VFGS_HD void prefetch_l1(const uint8_t* p, bool pred)
 // Every lane walks the full line count of a stripe (the exchange is a warp-wide shuffle); lanes outside the picture
 // or past the end of a short last stripe neither load nor store.
 template <bool IN16, bool OUT8, int NSH, bool FOLD, bool SHIFT>
-VFGS_HD void gather_task_body(const FgsParams& p, smem_addr_t luts, smem_addr_t img, int f, int c, uint32_t q, int lane)
+VFGS_HD void gather_task_body(const FgsParams& p, smem_addr_t luts, smem_addr_t img, int f, int c, uint32_t q, int lane, uint32_t next_q)
 {
 	constexpr bool PAIR = NSH == 4;
 	static_assert(PAIR || !SHIFT, "the shifted numbering exists for 16-sample blocks only");
@@ -310,8 +329,7 @@ VFGS_HD void gather_task_body(const FgsParams& p, smem_addr_t luts, smem_addr_t 
 	uint32_t raw[LB][4] = {}, vh[LB];
 #pragma unroll
 	for (int qq = 0; qq < LB; qq++) {
-		if (IN16) ld_global_16_if(src + qq * in_pitch, raw[qq], qq < nl);
-		else ld_global_8_if(src + qq * in_pitch, raw[qq], qq < nl);
+		gather_ld_if<IN16>(src + qq * in_pitch, raw[qq], qq < nl);
 		vh[qq] = SHIFT ? 0u : ld_sample_if<IB>(src + qq * in_pitch + halo_off, mem_halo && qq < nl);
 	}
 	if (VFGS_GATHER_PREFETCH > 0) {
@@ -388,8 +406,7 @@ VFGS_HD void gather_task_body(const FgsParams& p, smem_addr_t luts, smem_addr_t 
 			uint32_t w[4];
 			gather_finish<IN16, OUT8>(L, raw[qq], g, sc, w);
 			const bool more = line + LB < nl;
-			if (IN16) ld_global_16_if(nxt, raw[qq], more);
-			else ld_global_8_if(nxt, raw[qq], more);
+			gather_ld_if<IN16>(nxt, raw[qq], more);
 			if (!SHIFT) vh[qq] = ld_sample_if<IB>(nxt + halo_off, mem_halo && more);
 			if (VFGS_GATHER_PREFETCH > 0) prefetch_l1(nxt + VFGS_GATHER_PREFETCH * in_pitch, line + LB + VFGS_GATHER_PREFETCH < nl);
 			if (line < nl && stores) {
@@ -400,26 +417,40 @@ VFGS_HD void gather_task_body(const FgsParams& p, smem_addr_t luts, smem_addr_t 
 		}
 	};
 	group(0, std::true_type());
+	if (VFGS_GATHER_XPREFETCH > 0 && next_q) { // the first lines of this warp's next task (same component and frame), while this one runs
+		const long long u2 = (long long)next_q * 32 + lane - (SHIFT ? 1 : 0);
+		if (u2 < (long long)upr * (uint32_t)p.rows) {
+			const uint32_t row2 = fastdiv((uint32_t)u2, p.div_gunits[c]);
+			const int k2 = (int)((uint32_t)u2 - row2 * upr) * kSamplesPerLane;
+			const int cl2 = ((p.row_begin + (int)row2) * 16) >> ysh;
+			const uint8_t* s2 = pl.in + (long long)f * p.in_frame_bytes + (long long)cl2 * in_pitch + (long long)k2 * IB;
+#pragma unroll
+			for (int qq = 0; qq < VFGS_GATHER_XPREFETCH; qq++) prefetch_l1(s2 + qq * in_pitch, k2 < pl.width && cl2 + qq < pl.lines);
+		}
+	}
 #pragma unroll 1
 	for (int base = LB; base < lines; base += LB) group(base, std::false_type());
 }
 
 // Gather-kernel task numbering: per frame the gather components one after the other, each cut into warp-tasks of
 // 32 consecutive flat units.
+// task_stride: distance to the same warp's next task (0: unknown, no cross-task prefetch)
 template <bool IN16, bool OUT8, bool FOLD, bool SHIFT>
-VFGS_HD void process_task_gather(const FgsParams& p, smem_addr_t luts, smem_addr_t img, uint32_t task, int lane)
+VFGS_HD void process_task_gather(const FgsParams& p, smem_addr_t luts, smem_addr_t img, uint32_t task, int lane, uint32_t task_stride = 0)
 {
 	const int f = (int)fastdiv(task, p.div_gtasks);
 	uint32_t q = task - (uint32_t)f * (uint32_t)p.gtasks_per_frame;
 	int c = 0;
 	if (q >= (uint32_t)p.gtasks[0]) { q -= (uint32_t)p.gtasks[0]; c = 1; }
 	if (c == 1 && q >= (uint32_t)p.gtasks[1]) { q -= (uint32_t)p.gtasks[1]; c = 2; }
+	// the next task of this warp, when it lies in the same component of the same frame (else 0)
+	const uint32_t next_q = (task_stride && q + task_stride < (uint32_t)p.gtasks[c]) ? q + task_stride : 0u;
 #if !defined(__CUDA_ARCH__)
 	emu_warp().lane = lane; emu_warp().point = 0;
 #endif
-	if (SHIFT) gather_task_body<IN16, OUT8, 4, FOLD, true>(p, luts, img, f, c, q, lane); // the host never sends 8-sample blocks here
-	else if (c && p.subx > 1) gather_task_body<IN16, OUT8, 3, FOLD, false>(p, luts, img, f, c, q, lane);
-	else gather_task_body<IN16, OUT8, 4, FOLD, false>(p, luts, img, f, c, q, lane);
+	if (SHIFT) gather_task_body<IN16, OUT8, 4, FOLD, true>(p, luts, img, f, c, q, lane, next_q); // the host never sends 8-sample blocks here
+	else if (c && p.subx > 1) gather_task_body<IN16, OUT8, 3, FOLD, false>(p, luts, img, f, c, q, lane, next_q);
+	else gather_task_body<IN16, OUT8, 4, FOLD, false>(p, luts, img, f, c, q, lane, next_q);
 }
 
 } // namespace vfgs

@@ -9,6 +9,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -139,6 +140,8 @@ int set_err(int code, const char* fmt, ...)
 // ------------------------------------------------------------------------------------ device ctx
 int ensure_ctx(int device)
 {
+	static std::mutex mu; // the frame pipeline creates the context on its GPU-stage thread (yuv_pipeline.h)
+	std::lock_guard<std::mutex> lock(mu);
 	Context& c = g_ctx;
 	if (c.ready && (device < 0 || device == c.device)) {
 		CUDA_TRY(cudaSetDevice(c.device));

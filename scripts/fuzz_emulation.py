@@ -19,7 +19,7 @@ import numpy as np  # noqa: E402
 from oracle.pyoracle import RefState, _ptr  # noqa: E402
 from tests.util import Oracle, build_emu, first_mismatch, program_random_state, synth_frames  # noqa: E402
 
-WIDTHS = [136, 144, 152, 160, 200, 256, 264, 272, 512, 520, 528, 1040]
+WIDTHS = [136, 144, 152, 160, 200, 203, 256, 264, 270, 272, 366, 512, 520, 523, 528, 1040]
 
 
 def one_case(emu, rng):

@@ -23,11 +23,11 @@ struct StateDump { // == refh_state / oracle_dump
 	int scale_shift, bs, y_min, y_max, c_min, c_max, csubx, csuby;
 };
 
-template <bool IN16, bool OUT8>
+template <bool IN16, bool OUT8, bool EDGE>
 void run_fast(const FgsParams& p, const uint8_t* lut)
 {
 	for (long long task = 0; task < p.total_tasks; task++)
-		for (int lane = 0; lane < 32; lane++) process_task_fast<IN16, OUT8>(p, smem_addr(lut), (uint32_t)task, lane);
+		for (int lane = 0; lane < 32; lane++) process_task_fast<IN16, OUT8, EDGE>(p, smem_addr(lut), (uint32_t)task, lane);
 }
 
 // the gather task code exchanges grain values between lanes (warp shuffle on the device): every task runs twice,
@@ -57,7 +57,8 @@ extern "C" long long emu_octet_lines(void) { const long long v = emu_warp().octe
 
 // Packed planar frames, whole frames, like vfgs_b200_add_grain_frames_device.
 // mode: 0 automatic kernel choice, 1 general task code everywhere, 2 gather task code wherever it can
-// run (plan_launches). Returns a bit mask: 1 = fast, 2 = general, 4 = gather task code ran, 8 = with sign-folded slot copies, 16 = with the shifted unit numbering (in place).
+// run (plan_launches). Returns a bit mask: 1 = fast, 2 = general, 4 = gather task code ran, 8 = with sign-folded slot copies, 16 = with the shifted unit numbering (in place),
+// 32 = the fast task code's EDGE variant ran (ragged / unaligned rows).
 extern "C" int emu_add_grain_frames(const void* state, const void* in, void* out, int nframes, int width,
                                     int height, int out_depth, int first_frame_index, int mode)
 {
@@ -141,9 +142,19 @@ extern "C" int emu_add_grain_frames(const void* state, const void* in, void* out
 		for (int c = 0; c < 3; c++)
 			if (f.fimg_bytes[c]) memcpy(lut_ptr + f.fimg_off[c], fblob.data() + f.fimg_src[c], (size_t)f.fimg_bytes[c]);
 		expand_fast_luts((uint32_t*)lut_ptr, (const uint32_t*)fblob.data(), (uint32_t)(1 << (16 - h.scale_shift)), 0, 1);
-		if (isz == 1) run_fast<false, false>(f, lut_ptr);
-		else if (osz == 1) run_fast<true, true>(f, lut_ptr);
-		else run_fast<true, false>(f, lut_ptr);
+		if (isz == 1) run_fast<false, false, false>(f, lut_ptr);
+		else if (osz == 1) run_fast<true, true, false>(f, lut_ptr);
+		else run_fast<true, false, false>(f, lut_ptr);
+	}
+	if (lp.any_edge) { // the EDGE launch of the fast kernel: same shared-memory image, its own components
+		const FgsParams& f = lp.edge;
+		f_check(f.fpad == kEmuPad && f.fsmem <= kEmuPad + 3 * kLutBytes + (int)fblob.size());
+		for (int c = 0; c < 3; c++)
+			if (f.fimg_bytes[c]) memcpy(lut_ptr + f.fimg_off[c], fblob.data() + f.fimg_src[c], (size_t)f.fimg_bytes[c]);
+		expand_fast_luts((uint32_t*)lut_ptr, (const uint32_t*)fblob.data(), (uint32_t)(1 << (16 - h.scale_shift)), 0, 1);
+		if (isz == 1) run_fast<false, false, true>(f, lut_ptr);
+		else if (osz == 1) run_fast<true, true, true>(f, lut_ptr);
+		else run_fast<true, false, true>(f, lut_ptr);
 	}
 	if (lp.any_gather) {
 		// what fgs_apply_gather_kernel builds in shared memory: one private LUT per gather component, then the image
@@ -168,7 +179,7 @@ extern "C" int emu_add_grain_frames(const void* state, const void* in, void* out
 	if (lp.any_general)
 		for (long long task = 0; task < lp.general.total_tasks; task++)
 			for (int lane = 0; lane < 32; lane++) process_task(lp.general, tab, (uint32_t)task, lane);
-	return (lp.any_fast ? 1 : 0) | (lp.any_general ? 2 : 0) | (lp.any_gather ? 4 : 0) | (lp.any_gather && lp.gather_fold ? 8 : 0) | (lp.any_gather && lp.gather_shift ? 16 : 0);
+	return (lp.any_fast ? 1 : 0) | (lp.any_general ? 2 : 0) | (lp.any_gather ? 4 : 0) | (lp.any_gather && lp.gather_fold ? 8 : 0) | (lp.any_gather && lp.gather_shift ? 16 : 0) | (lp.any_edge ? 32 : 0);
 }
 
 // Launch planning of a whole-frame call, without running anything (host logic only): which kernel serves each

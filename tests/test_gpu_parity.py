@@ -329,7 +329,8 @@ def test_out_of_range_codes_and_minus_128_pattern(hw):
     assert np.array_equal(got, o.add_grain_frames(frames, n, w, h, 0))
 
 
-@pytest.mark.parametrize("w,h,n", [(144, 1, 2), (144, 15, 3), (136, 16, 2), (160, 17, 2), (130, 31, 1), (16384, 18, 1), (8200, 20, 1)])
+@pytest.mark.parametrize("w,h,n", [(144, 1, 2), (144, 15, 3), (136, 16, 2), (160, 17, 2), (130, 31, 1), (16384, 18, 1), (8200, 20, 1),
+                                   (1366, 768, 2), (1928, 1080, 1), (203, 30, 2), (366, 19, 3)])
 def test_extreme_geometries(hw, w, h, n):
     """Smallest legal width, single-line and single-block-row pictures (R = 1), odd heights, very wide rows."""
     for case in ("fgs_afgs1_test1.cfg|d10|420|g100", "fgs_sei.cfg|d10|420|g100", "fgs_sei_ff_test4.cfg|d10|444|g150"):
@@ -353,7 +354,7 @@ def test_random_states(hw, spec):
     """Random hardware states through the setters (formats, depths, pattern counts, shifts and ranges the cfg/
     files do not reach: 8-bit 4:2:2 / 4:4:4, multi-pattern 4:4:4 chroma, -128 pattern bytes): every kernel == oracle."""
     seed, depth, fmt = spec[0], spec[1], spec[2]
-    for (w, h, n) in ((520, 50, 2), (1024, 96, 1)):
+    for (w, h, n) in ((520, 50, 2), (1024, 96, 1), (366, 34, 2), (203, 18, 1)):
         for od in ((0, 8) if depth == 10 else (0,)):
             frames = synth_frames(n, w, h, fmt, depth, seed=seed + od)
             o = Oracle(); program_random_state(o, *spec)

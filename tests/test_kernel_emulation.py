@@ -82,8 +82,9 @@ def test_fast_path_is_taken_where_expected(emu):
     assert mask_of("fgs_sei_ff_test1.cfg|d8|420|g100", 512, 64) == 1
     assert mask_of("fgs_sei.cfg|d10|420|g100", 512, 64) == 13          # luma: gather (sign-folded slot copies), chroma: fast
     assert mask_of("fgs_sei_ff_test5.cfg|d10|420|g100", 512, 64) == 13  # chroma: gather
-    assert mask_of("fgs_afgs1_test1.cfg|d10|420|g100", 200, 64) == 3   # luma rows qualify, chroma width 100 does not
-    assert mask_of("fgs_afgs1_test1.cfg|d10|420|g100", 204, 64) == 2
+    assert mask_of("fgs_afgs1_test1.cfg|d10|420|g100", 200, 64) == 33  # luma rows qualify, chroma width 100 takes the fast code's EDGE variant
+    assert mask_of("fgs_afgs1_test1.cfg|d10|420|g100", 204, 64) == 32  # ragged everywhere: EDGE variant for all three
+    assert mask_of("fgs_sei.cfg|d10|420|g100", 204, 64) == 34          # sample-adaptive luma on ragged rows: general code
 
 
 def test_fast_path_garbage_samples_and_minus_128(emu):
@@ -104,7 +105,8 @@ def test_fast_path_garbage_samples_and_minus_128(emu):
     assert mask == 5 and np.array_equal(got, o.add_grain_frames(frames, n, w, h, 0))  # gather code, sign by multiplication
 
 
-@pytest.mark.parametrize("w,h,n", [(144, 1, 2), (144, 15, 3), (136, 16, 2), (160, 17, 2), (130, 31, 1), (16384, 18, 1), (8200, 20, 1)])
+@pytest.mark.parametrize("w,h,n", [(144, 1, 2), (144, 15, 3), (136, 16, 2), (160, 17, 2), (130, 31, 1), (16384, 18, 1), (8200, 20, 1),
+                                   (1366, 40, 2), (1928, 24, 1), (203, 30, 2), (366, 19, 3)])
 def test_extreme_geometries(emu, w, h, n):
     """Smallest legal width (> 128, vfgs_hw.c:168), pictures of a single line / a single block-row (R = 1:
     the LFSR does not advance between frames), odd heights, and the widest rows the oracle supports."""

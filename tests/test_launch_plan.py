@@ -49,9 +49,9 @@ def test_kernel_choice(emu):
     assert plan(emu, o5, 512, 64)["kind"] == [FAST, GATHER, GATHER]
     assert plan(emu, o5, 512, 64, in_place=1)["kind"] == [FAST, GENERAL, GENERAL]  # halo lanes would read overwritten input: the shim takes the scratch route
     assert plan(emu, o, 512, 64, mode=1)["kind"] == [GENERAL] * 3
-    assert plan(emu, o, 204, 64)["kind"] == [GENERAL] * 3                  # 204 % 8 != 0, chroma rows unaligned
+    assert plan(emu, o, 204, 64)["kind"] == [GENERAL, 3, 3]                # 204 % 8 != 0: sample-adaptive luma on the general kernel, chroma on the fast kernel's EDGE variant
     o = Oracle(); program_case(o, G, "fgs_afgs1_test1.cfg|d10|420|g100")
-    assert plan(emu, o, 200, 64)["kind"] == [FAST, GENERAL, GENERAL]       # chroma width 100
+    assert plan(emu, o, 200, 64)["kind"] == [FAST, 3, 3]                   # chroma width 100: EDGE variant
     assert plan(emu, o, 512, 64, mode=2)["kind"] == [GATHER] * 3
 
 

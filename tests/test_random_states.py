@@ -11,7 +11,7 @@ from oracle import pyoracle
 from oracle.pyoracle import RefState, _ptr
 from tests.util import RANDOM_STATES, Oracle, build_emu, first_mismatch, program_random_state, synth_frames
 
-SIZES = ((264, 40, 2), (520, 34, 1), (544, 36, 2))  # 544: multiple of 32, so 8-bit components take the 16-samples-per-lane path
+SIZES = ((264, 40, 2), (520, 34, 1), (544, 36, 2), (366, 21, 2), (203, 18, 1))  # 544: multiple of 32, so 8-bit components take the 16-samples-per-lane path
 
 
 @pytest.mark.skipif(not pyoracle.have_reference(), reason="needs oracle/_ref (the compiled reference)")

@@ -162,7 +162,7 @@ class VfgsHw:
     def last_launch(self) -> dict:
         a = (C.c_int * 5)()
         self.L.vfgs_b200_last_launch(a)
-        kernels = [n for bit, n in ((1, "fgs_apply_fast_kernel"), (4, "fgs_apply_gather_kernel"), (2, "fgs_apply_kernel")) if a[4] & bit]
+        kernels = [n for bit, n in ((1, "fgs_apply_fast_kernel"), (8, "fgs_apply_fast_kernel<EDGE>"), (4, "fgs_apply_gather_kernel"), (2, "fgs_apply_kernel")) if a[4] & bit]
         return {"grid": a[0], "block": a[1], "smem": a[2], "sms": a[3], "kernels": kernels}
 
     def state(self) -> dict:

@@ -226,6 +226,153 @@ VFGS_HD void octet(smem_addr_t a, uint32_t& w0, uint32_t& w1)
 	else { w0 = lds32(a); w1 = lds32(a + 4); }
 }
 
+// ---- rows at any address, ragged widths (EDGE variant) ---------------------------------------
+// The packed .yuv layout (src/yuv.c:162-214: stride = width) puts a row wherever the previous one ended: with a width
+// that is not a multiple of 8 samples (1366 x 768, the 964-sample chroma rows of 1928 x 1080) row starts cycle through
+// every alignment the sample size allows, and the last lane unit of a row is partial. A lane unit is still 8 samples
+// that never straddle a block; only the way its bytes travel changes: the largest naturally aligned pieces the
+// address allows (16 bytes at offset 0 of a 16-byte line; 4 + 8 + 4 at offsets 4 and 12; 8 + 8 at offset 8;
+// 2 + 4 + 4 + 4 + 2 at the odd multiples of 2), each piece one coalesced warp-wide access. A partial unit goes
+// sample by sample. N = bytes of a full unit (16: 16-bit samples, 8: 8-bit samples), nv = valid samples (1..8).
+VFGS_HD void ld_piece16(const uint8_t* p, uint32_t* r)
+{
+#if defined(__CUDA_ARCH__)
+	const uint4 v = *(const uint4*)p; r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+#else
+	memcpy(r, p, 16);
+#endif
+}
+VFGS_HD void ld_piece8(const uint8_t* p, uint32_t* r)
+{
+#if defined(__CUDA_ARCH__)
+	const uint2 v = *(const uint2*)p; r[0] = v.x; r[1] = v.y;
+#else
+	memcpy(r, p, 8);
+#endif
+}
+// (the callers guarantee natural alignment; the host build must not rely on it being exploitable)
+VFGS_HD uint32_t ld_piece4(const uint8_t* p)
+{
+#if defined(__CUDA_ARCH__)
+	return *(const uint32_t*)p;
+#else
+	uint32_t v; memcpy(&v, p, 4); return v;
+#endif
+}
+VFGS_HD uint32_t ld_piece2(const uint8_t* p)
+{
+#if defined(__CUDA_ARCH__)
+	return *(const uint16_t*)p;
+#else
+	uint16_t v; memcpy(&v, p, 2); return v;
+#endif
+}
+VFGS_HD void st_piece16(uint8_t* p, const uint32_t* w)
+{
+#if defined(__CUDA_ARCH__)
+	*(uint4*)p = make_uint4(w[0], w[1], w[2], w[3]);
+#else
+	memcpy(p, w, 16);
+#endif
+}
+VFGS_HD void st_piece8(uint8_t* p, uint32_t w0, uint32_t w1)
+{
+#if defined(__CUDA_ARCH__)
+	*(uint2*)p = make_uint2(w0, w1);
+#else
+	memcpy(p, &w0, 4); memcpy(p + 4, &w1, 4);
+#endif
+}
+VFGS_HD void st_piece4(uint8_t* p, uint32_t w)
+{
+#if defined(__CUDA_ARCH__)
+	*(uint32_t*)p = w;
+#else
+	memcpy(p, &w, 4);
+#endif
+}
+VFGS_HD void st_piece2(uint8_t* p, uint32_t w)
+{
+	const uint16_t v = (uint16_t)w;
+#if defined(__CUDA_ARCH__)
+	*(uint16_t*)p = v;
+#else
+	memcpy(p, &v, 2);
+#endif
+}
+
+template <int N>
+VFGS_HD void edge_load(const uint8_t* p, uint32_t r[4], int nv)
+{
+	constexpr int SB = N / 8; // bytes per sample
+	r[0] = r[1] = r[2] = r[3] = 0;
+	if (nv < 8) { // samples right of the picture read as 0
+#pragma unroll
+		for (int e = 0; e < 8; e++) {
+			if (e < nv) {
+				const uint32_t v = SB == 2 ? ld_piece2(p + 2 * e) : (uint32_t)p[e];
+				if (SB == 2) r[e >> 1] |= v << (16 * (e & 1));
+				else r[e >> 2] |= v << (8 * (e & 3));
+			}
+		}
+		return;
+	}
+	const unsigned a = (unsigned)((uintptr_t)p & (N - 1));
+	if (N == 16) {
+		if (a == 0) ld_piece16(p, r);
+		else if (a == 8) { ld_piece8(p, r); ld_piece8(p + 8, r + 2); }
+		else if ((a & 3) == 0) { r[0] = ld_piece4(p); ld_piece8(p + 4, r + 1); r[3] = ld_piece4(p + 12); }
+		else { // odd multiple of 2
+			const uint32_t h0 = ld_piece2(p), m0 = ld_piece4(p + 2), m1 = ld_piece4(p + 6), m2 = ld_piece4(p + 10), h1 = ld_piece2(p + 14);
+			r[0] = h0 | (m0 << 16); r[1] = prmt(m0, m1, 0x5432); r[2] = prmt(m1, m2, 0x5432); r[3] = (m2 >> 16) | (h1 << 16);
+		}
+	} else {
+		if (a == 0) ld_piece8(p, r);
+		else if (a == 4) { r[0] = ld_piece4(p); r[1] = ld_piece4(p + 4); }
+		else if ((a & 1) == 0) {
+			const uint32_t h0 = ld_piece2(p), m = ld_piece4(p + 2), h1 = ld_piece2(p + 6);
+			r[0] = h0 | (m << 16); r[1] = (m >> 16) | (h1 << 16);
+		} else {
+#pragma unroll
+			for (int e = 0; e < 8; e++) r[e >> 2] |= (uint32_t)p[e] << (8 * (e & 3));
+		}
+	}
+}
+template <int N>
+VFGS_HD void edge_store(uint8_t* p, const uint32_t w[4], int nv)
+{
+	constexpr int SB = N / 8;
+	if (nv < 8) {
+#pragma unroll
+		for (int e = 0; e < 8; e++) {
+			if (e < nv) {
+				if (SB == 2) st_piece2(p + 2 * e, w[e >> 1] >> (16 * (e & 1)));
+				else p[e] = (uint8_t)(w[e >> 2] >> (8 * (e & 3)));
+			}
+		}
+		return;
+	}
+	const unsigned a = (unsigned)((uintptr_t)p & (N - 1));
+	if (N == 16) {
+		if (a == 0) st_piece16(p, w);
+		else if (a == 8) { st_piece8(p, w[0], w[1]); st_piece8(p + 8, w[2], w[3]); }
+		else if ((a & 3) == 0) { st_piece4(p, w[0]); st_piece8(p + 4, w[1], w[2]); st_piece4(p + 12, w[3]); }
+		else {
+			st_piece2(p, w[0]);
+			st_piece4(p + 2, prmt(w[0], w[1], 0x5432)); st_piece4(p + 6, prmt(w[1], w[2], 0x5432)); st_piece4(p + 10, prmt(w[2], w[3], 0x5432));
+			st_piece2(p + 14, w[3] >> 16);
+		}
+	} else {
+		if (a == 0) st_piece8(p, w[0], w[1]);
+		else if (a == 4) { st_piece4(p, w[0]); st_piece4(p + 4, w[1]); }
+		else if ((a & 1) == 0) { st_piece2(p, w[0]); st_piece4(p + 2, prmt(w[0], w[1], 0x5432)); st_piece2(p + 6, w[1] >> 16); }
+		else {
+#pragma unroll
+			for (int e = 0; e < 8; e++) p[e] = (uint8_t)(w[e >> 2] >> (8 * (e & 3)));
+		}
+	}
+}
+
 // Per-lane constants of a warp-task (pattern addresses have the block's sign folded in).
 // Halo bytes feed the block-edge filter. With 16-sample blocks a lane holds one half of a block and has
 // exactly one block edge (its left end if it is the first half, else its right end), so one halo address
@@ -397,10 +544,10 @@ VFGS_HD uint32_t window_offset(uint32_t s, const WoffComp& w)
 #endif
 constexpr int kFastLB = VFGS_FAST_LB; // lines in flight per lane (build-time knob for experiments)
 #ifndef VFGS_FAST_PREFETCH16
-#define VFGS_FAST_PREFETCH16 0 // lines ahead of the line loads prefetched into L1, 16-bit output (build-time knob for experiments)
+#define VFGS_FAST_PREFETCH16 4 // lines ahead of the line loads prefetched into L1, 16-bit output: 1080p 0.867 -> 0.911, 4K 0.893 -> 0.918 of the HBM peak (profiles/r02_fast_prefetch_ab.md); 8 lines: no better
 #endif
 #ifndef VFGS_FAST_PREFETCH8
-#define VFGS_FAST_PREFETCH8 0  // same, 8-bit output
+#define VFGS_FAST_PREFETCH8 0  // same, 8-bit output: the issue-bound variant loses with it (0.786 -> 0.743)
 #endif
 static_assert(kFastLB >= 2, "both vertical-overlap lines of a block-row must fall into the first group of lines");
 #ifndef VFGS_FAST_LB16
@@ -410,7 +557,8 @@ static_assert(kFastLB >= 2, "both vertical-overlap lines of a block-row must fal
 #define VFGS_FAST_LB8 VFGS_FAST_LB  // fast kernel, 16-bit in, 8-bit out
 #endif
 
-template <bool IN16, bool OUT8, int NSH>
+// EDGE: rows at any sample-aligned address, partial last unit of a row (see edge_load / edge_store above)
+template <bool IN16, bool OUT8, int NSH, bool EDGE = false>
 VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, const TaskGeom& t, int k0, int lane)
 {
 	const int c = t.c;
@@ -437,15 +585,17 @@ VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, const TaskGeom&
 
 	// The first LB lines are requested before anything else: the block decode below runs
 	// while they are in flight. A stripe shorter than LB lines re-reads its last line.
+	const int nv = EDGE ? (pl.width - k0 < kSamplesPerLane ? pl.width - k0 : kSamplesPerLane) : kSamplesPerLane; // valid samples of this unit
 	uint32_t raw[LB][4];
 #pragma unroll
 	for (int q = 0; q < LB; q++) {
 		const int qq = q < nl ? q : nl - 1;
-		if (IN16) ld_samples_16<kL1>(src + qq * in_pitch, raw[q]);
+		if (EDGE) edge_load<IN16 ? 16 : 8>(src + qq * in_pitch, raw[q], nv);
+		else if (IN16) ld_samples_16<kL1>(src + qq * in_pitch, raw[q]);
 		else ld_global_8(src + qq * in_pitch, raw[q]);
 	}
 
-	if (IN16 && PF > 0) {
+	if (IN16 && PF > 0 && !EDGE) {
 #pragma unroll
 		for (int q = LB; q < LB + PF; q++) prefetch_l1(src + q * in_pitch, q < nl);
 	}
@@ -497,11 +647,13 @@ VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, const TaskGeom&
 				fast_line<IN16, OUT8, NSH>(L, rc, w_cur, w_up, U, ru, raw[q], w);
 				// this slot's registers are free again: request the line LB further down
 				const bool refill = WHOLE ? more : line + LB < nl;
-				if (IN16) ld_samples_16_if<kL1>(nxt, raw[q], refill);
+				if (EDGE) { if (refill) edge_load<IN16 ? 16 : 8>(nxt, raw[q], nv); }
+				else if (IN16) ld_samples_16_if<kL1>(nxt, raw[q], refill);
 				else ld_global_8_if(nxt, raw[q], refill);
-				if (IN16 && PF > 0) prefetch_l1(nxt + PF * in_pitch, line + LB + PF < nl);
+				if (IN16 && PF > 0 && !EDGE) prefetch_l1(nxt + PF * in_pitch, line + LB + PF < nl);
 				if (WHOLE || line < nl) {
-					if (OB == 2) st_global_16(dst, w);
+					if (EDGE) edge_store<OB == 2 ? 16 : 8>(dst, w, nv);
+					else if (OB == 2) st_global_16(dst, w);
 					else st_global_8(dst, w);
 				}
 				rc += L.stride; nxt += in_pitch; dst += out_pitch;
@@ -652,7 +804,7 @@ VFGS_HD void wide_task_body(const FgsParams& p, smem_addr_t lut, const TaskGeom&
 // stripes' rows are one flat run of lane units (8 samples, or 16 on the wide 8-bit path: FgsParams::fwide), 32
 // consecutive units per warp-task, so only the very last task of a component can have idle lanes (a row need
 // not be a multiple of 256 samples).
-template <bool IN16, bool OUT8>
+template <bool IN16, bool OUT8, bool EDGE = false>
 VFGS_HD void process_task_fast(const FgsParams& p, smem_addr_t lut, uint32_t task, int lane)
 {
 	TaskGeom t;
@@ -667,15 +819,15 @@ VFGS_HD void process_task_fast(const FgsParams& p, smem_addr_t lut, uint32_t tas
 	const uint32_t row = fastdiv(unit, p.div_funits[t.c]);
 	t.r = p.row_begin + (int)row;
 	t.seg = 0;
-	if (!IN16 && p.fwide[t.c]) { // 8-bit samples, 16 per lane
+	if (!IN16 && !EDGE && p.fwide[t.c]) { // 8-bit samples, 16 per lane
 		const int k0 = (int)(unit - row * upr) * 16;
 		if (t.c && p.subx > 1) wide_task_body<3>(p, lut, t, k0, lane);
 		else wide_task_body<4>(p, lut, t, k0, lane);
 		return;
 	}
 	const int k0 = (int)(unit - row * upr) * kSamplesPerLane;
-	if (t.c && p.subx > 1) fast_task_body<IN16, OUT8, 3>(p, lut, t, k0, lane);
-	else fast_task_body<IN16, OUT8, 4>(p, lut, t, k0, lane);
+	if (t.c && p.subx > 1) fast_task_body<IN16, OUT8, 3, EDGE>(p, lut, t, k0, lane);
+	else fast_task_body<IN16, OUT8, 4, EDGE>(p, lut, t, k0, lane);
 }
 
 } // namespace vfgs

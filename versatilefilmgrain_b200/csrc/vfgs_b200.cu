@@ -310,7 +310,7 @@ void fill_common(FgsParams& p, const Geometry& g)
 }
 
 typedef void (*GrainKernel)(const FgsParams);
-enum KernelKind { kGeneral = 0, kFast = 1, kGather = 2 };
+enum KernelKind { kGeneral = 0, kFast = 1, kGather = 2, kFastEdge = 3 };
 
 template <bool FOLD, bool SHIFT>
 GrainKernel gather_kernel(const FgsParams& p)
@@ -332,14 +332,21 @@ int launch_apply(const FgsParams& p, cudaStream_t stream, KernelKind kind = kGen
 	if (p.total_tasks >= (1ll << 31)) return set_err(VFGS_B200_ERR_ARG, "batch too large for one launch (%lld warp-tasks): split the call", p.total_tasks);
 	GrainKernel kern = fgs_apply_kernel;
 	int threads = kCtaThreads, smem = p.blob_bytes;
-	if (kind == kFast) {
-		kern = p.in_bytes == 1 ? fgs_apply_fast_kernel<false, false>
-		     : p.out_bytes == 1 ? fgs_apply_fast_kernel<true, true> : fgs_apply_fast_kernel<true, false>;
+	if (kind == kFast || kind == kFastEdge) {
+		if (kind == kFast)
+			kern = p.in_bytes == 1 ? fgs_apply_fast_kernel<false, false>
+			     : p.out_bytes == 1 ? fgs_apply_fast_kernel<true, true> : fgs_apply_fast_kernel<true, false>;
+		else
+			kern = p.in_bytes == 1 ? fgs_apply_fast_kernel<false, false, true>
+			     : p.out_bytes == 1 ? fgs_apply_fast_kernel<true, true, true> : fgs_apply_fast_kernel<true, false, true>;
 		threads = fast_threads(p.in_bytes == 2, p.in_bytes == 2 && p.out_bytes == 1); smem = p.fsmem;
 		if (smem > c.fast_smem_attr) {
 			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_fast_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_fast_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_fast_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_fast_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_fast_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_fast_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 			c.fast_smem_attr = smem;
 		}
 	} else if (kind == kGather) {
@@ -378,7 +385,7 @@ int launch_apply(const FgsParams& p, cudaStream_t stream, KernelKind kind = kGen
 	if (c.timing) CUDA_TRY(cudaEventRecord(e1, stream));
 	g_launches++;
 	c.last_launch[0] = grid; c.last_launch[1] = threads; c.last_launch[2] = smem; c.last_launch[3] = c.sm_count;
-	c.last_launch[4] |= kind == kFast ? 1 : kind == kGather ? 4 : 2;
+	c.last_launch[4] |= kind == kFast ? 1 : kind == kGather ? 4 : kind == kFastEdge ? 8 : 2;
 	return VFGS_B200_OK;
 }
 
@@ -457,7 +464,7 @@ int run_frames_device(const vfgs_b200_planes& in, const vfgs_b200_planes& out, i
 	plan_frames(in, out, n, g, in_place, d_streams, p, lp, d_woffs);
 	g_ctx.last_launch[4] = 0;
 	// the register table feeds the general kernel, the window-offset table the fast and gather kernels
-	if (int rc = launch_streams(epoch, lp.any_general ? d_streams : nullptr, (lp.any_fast || lp.any_gather) ? d_woffs : nullptr,
+	if (int rc = launch_streams(epoch, lp.any_general ? d_streams : nullptr, (lp.any_fast || lp.any_gather || lp.any_edge) ? d_woffs : nullptr,
 	                            make_woff_params(p, lp.kind), n, g, frame0, table_stream ? table_stream : stream)) return rc;
 	if (table_stream) { // the tables were computed beside the caller's stream: the grain kernels wait for them
 		CUDA_TRY(cudaEventRecord(table_ready, table_stream));
@@ -466,6 +473,8 @@ int run_frames_device(const vfgs_b200_planes& in, const vfgs_b200_planes& out, i
 	if (int rc = images_before(stream)) return rc;
 	if (lp.any_fast)
 		if (int rc = launch_apply(lp.fast, stream, kFast)) return rc;
+	if (lp.any_edge)
+		if (int rc = launch_apply(lp.edge, stream, kFastEdge)) return rc;
 	if (lp.any_gather)
 		if (int rc = launch_apply(lp.gather, stream, kGather, lp.gather_smem, lp.gather_fold, lp.gather_shift)) return rc;
 	if (lp.any_general)

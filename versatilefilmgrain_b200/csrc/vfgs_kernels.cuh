@@ -128,7 +128,8 @@ fgs_apply_kernel(const __grid_constant__ FgsParams p)
 		process_task(p, tab, (uint32_t)task, lane);
 }
 
-// Fast path: single-pattern components, aligned rows (fgs_fast.h). One 1024-thread persistent CTA per
+// Fast path: single-pattern components (fgs_fast.h); EDGE: the variant for rows at any sample-aligned address and
+// widths that are not a multiple of 8 samples (packed ragged pictures), everything else identical. One 1024-thread persistent CTA per
 // SM (measured faster than 2 x 512: one table image per SM, more of the unified array left to L1, which
 // the 16-bit-output variant uses as its landing buffer for the lines in flight).
 // Shared memory: three per-lane replicated LUTs of scale << (16 - shift) (3 x 32 KB, each on a 32 KB
@@ -154,7 +155,7 @@ template <bool IN16, bool OUT8> struct FastCta {
 };
 inline int fast_threads(bool in16, bool out8) { return !in16 ? VFGS_FAST_THREADS_IN8 : out8 ? VFGS_FAST_THREADS8 : VFGS_FAST_THREADS16; }
 
-template <bool IN16, bool OUT8>
+template <bool IN16, bool OUT8, bool EDGE = false>
 __global__ void __launch_bounds__(FastCta<IN16, OUT8>::threads, 1)
 fgs_apply_fast_kernel(const __grid_constant__ FgsParams p)
 {
@@ -188,7 +189,7 @@ fgs_apply_fast_kernel(const __grid_constant__ FgsParams p)
 	const smem_addr_t lut = smem_addr(lut_ptr);
 	const long long stride = (long long)gridDim.x * kFastWarps;
 	for (long long task = (long long)blockIdx.x * kFastWarps + (threadIdx.x >> 5); task < p.total_tasks; task += stride)
-		process_task_fast<IN16, OUT8>(p, lut, (uint32_t)task, lane);
+		process_task_fast<IN16, OUT8, EDGE>(p, lut, (uint32_t)task, lane);
 }
 
 // Gather path: components with sample-adaptive pattern selection (fgs_gather.h). Shared memory: one

@@ -240,9 +240,9 @@ inline void place_fast_images(FgsParams& p, const TableInfo& bi, int pad, const 
 // mode: 0 = as above, 1 = general kernel for everything, 2 = gather kernel wherever it can run
 // (1 and 2 exist for the tests). smem_limit: opt-in shared memory per block of the device.
 struct LaunchPlan {
-	FgsParams fast, gather, general;
-	bool any_fast, any_gather, any_general;
-	int kind[3];     // per component: 0 fast, 1 gather, 2 general kernel
+	FgsParams fast, gather, general, edge;
+	bool any_fast, any_gather, any_general, any_edge;
+	int kind[3];     // per component: 0 fast, 1 gather, 2 general kernel, 3 fast kernel's EDGE variant (ragged / unaligned rows)
 	int gather_smem; // dynamic shared memory of the gather launch
 	bool gather_fold; // the gather launch reads sign-folded slot copies (fgs_gather.h, FOLD)
 	bool gather_shift; // in-place call: the gather launch uses the shifted unit numbering (fgs_gather.h, SHIFT)
@@ -250,8 +250,8 @@ struct LaunchPlan {
 
 inline void plan_launches(const FgsParams& p, const TableInfo& bi, int mode, bool in_place, int smem_limit, int fast_pad, LaunchPlan& lp)
 {
-	lp.fast = lp.gather = lp.general = p;
-	lp.any_fast = lp.any_gather = lp.any_general = false;
+	lp.fast = lp.gather = lp.general = lp.edge = p;
+	lp.any_fast = lp.any_gather = lp.any_general = lp.any_edge = false;
 	int* kind = lp.kind;
 	int ngather = 0;
 	for (int c = 0; c < 3; c++) {
@@ -265,15 +265,25 @@ inline void plan_launches(const FgsParams& p, const TableInfo& bi, int mode, boo
 			if (bi.fast_ok[c] && mode != 2) kind[c] = 0;
 			else if (!in_place || !block8) kind[c] = 1;
 		}
+#ifndef VFGS_NO_EDGE_KERNEL
+		// ragged width or rows that do not start on a vector boundary: the fast kernel's EDGE variant, provided every row
+		// starts on a sample boundary (always, for a sane buffer)
+		if (!aligned && mode == 0 && bi.fast_ok[c] &&
+		    aligned_for(p.comp[c].in, p.comp[c].in_row_bytes, p.in_frame_bytes, (size_t)p.in_bytes) &&
+		    aligned_for(p.comp[c].out, p.comp[c].out_row_bytes, p.out_frame_bytes, (size_t)p.out_bytes))
+			kind[c] = 3;
+#endif
 		if (kind[c] == 1) ngather++;
 	}
-	{ // the fast kernel's tables must fit as well
+	for (int which = 0; which < 2; which++) { // the fast kernel's tables must fit as well (plain launch, EDGE launch)
+		const int k = which ? 3 : 0;
+		FgsParams& f = which ? lp.edge : lp.fast;
 		bool served[3];
-		for (int c = 0; c < 3; c++) served[c] = kind[c] == 0;
-		place_fast_images(lp.fast, bi, fast_pad, served);
-		if (lp.fast.fsmem + 64 > smem_limit) {
-			for (int c = 0; c < 3; c++) if (kind[c] == 0) { kind[c] = 2; served[c] = false; }
-			place_fast_images(lp.fast, bi, fast_pad, served);
+		for (int c = 0; c < 3; c++) served[c] = kind[c] == k;
+		place_fast_images(f, bi, fast_pad, served);
+		if (f.fsmem + 64 > smem_limit) {
+			for (int c = 0; c < 3; c++) if (kind[c] == k) { kind[c] = 2; served[c] = false; }
+			place_fast_images(f, bi, fast_pad, served);
 		}
 	}
 	// sign folding needs the negated copies of every bank a gather component reads, and room for them
@@ -294,18 +304,21 @@ inline void plan_launches(const FgsParams& p, const TableInfo& bi, int mode, boo
 		if (kind[c] != 0) lp.fast.nseg[c] = 0;
 		if (kind[c] != 1) lp.gather.nseg[c] = 0;
 		if (kind[c] != 2) lp.general.nseg[c] = 0;
-		(kind[c] == 0 ? lp.any_fast : kind[c] == 1 ? lp.any_gather : lp.any_general) = true;
+		if (kind[c] != 3) lp.edge.nseg[c] = 0;
+		(kind[c] == 0 ? lp.any_fast : kind[c] == 1 ? lp.any_gather : kind[c] == 3 ? lp.any_edge : lp.any_general) = true;
 	}
-	// the fast kernel numbers its tasks over flat runs of lane units (process_task_fast)
-	{
-		FgsParams& f = lp.fast;
+	// the fast kernel numbers its tasks over flat runs of lane units (process_task_fast); the EDGE launch has a partial
+	// last unit per row where the width is not a multiple of 8
+	for (int which = 0; which < 2; which++) {
+		const int k = which ? 3 : 0;
+		FgsParams& f = which ? lp.edge : lp.fast;
 		f.ftasks_per_frame = 0;
 		for (int c = 0; c < 3; c++) {
 			// 8-bit samples: 16 per lane where the rows allow 128-bit accesses
-			f.fwide[c] = VFGS_FAST_WIDE8 && kind[c] == 0 && f.in_bytes == 1 && f.comp[c].width % 16 == 0 &&
+			f.fwide[c] = VFGS_FAST_WIDE8 && kind[c] == 0 && k == 0 && f.in_bytes == 1 && f.comp[c].width % 16 == 0 &&
 			             aligned_for(f.comp[c].in, f.comp[c].in_row_bytes, f.in_frame_bytes, 16) &&
 			             aligned_for(f.comp[c].out, f.comp[c].out_row_bytes, f.out_frame_bytes, 16);
-			f.funits_per_row[c] = kind[c] == 0 ? f.comp[c].width / (f.fwide[c] ? 16 : kSamplesPerLane) : 0;
+			f.funits_per_row[c] = kind[c] == k ? (f.comp[c].width + (f.fwide[c] ? 16 : kSamplesPerLane) - 1) / (f.fwide[c] ? 16 : kSamplesPerLane) : 0;
 			f.ftasks[c] = (f.funits_per_row[c] * f.rows + 31) / 32;
 			f.ftasks_per_frame += f.ftasks[c];
 			f.div_funits[c] = make_fastdiv((uint32_t)(f.funits_per_row[c] > 0 ? f.funits_per_row[c] : 1));
@@ -332,12 +345,13 @@ inline void plan_launches(const FgsParams& p, const TableInfo& bi, int mode, boo
 		}
 		g.div_gtasks = make_fastdiv((uint32_t)(g.gtasks_per_frame > 0 ? g.gtasks_per_frame : 1));
 	}
-	for (FgsParams* q : {&lp.fast, &lp.gather, &lp.general}) {
+	for (FgsParams* q : {&lp.fast, &lp.gather, &lp.general, &lp.edge}) {
 		q->tasks_per_stripe = q->nseg[0] + q->nseg[1] + q->nseg[2];
 		q->total_tasks = (long long)q->nframes * q->rows * q->tasks_per_stripe;
 		q->div_tps = make_fastdiv((uint32_t)(q->tasks_per_stripe > 0 ? q->tasks_per_stripe : 1));
 	}
 	lp.fast.total_tasks = (long long)lp.fast.nframes * lp.fast.ftasks_per_frame;
+	lp.edge.total_tasks = (long long)lp.edge.nframes * lp.edge.ftasks_per_frame;
 	lp.gather.total_tasks = (long long)lp.gather.nframes * lp.gather.gtasks_per_frame;
 }
 

@@ -88,20 +88,6 @@ VFGS_HD uint32_t index_bits(const uint32_t raw[4])
 	}
 }
 
-// base + (entry >> 8): the slot offset field of a LUT entry added to a window address, as ONE multiply-add on the FMA
-// pipe (mad.hi with k24 = 2^24) instead of a shift-add on the ALU pipe
-VFGS_HD smem_addr_t entry_address(uint32_t ent, uint32_t k24, smem_addr_t base)
-{
-#if defined(__CUDA_ARCH__)
-	uint32_t d;
-	asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(ent), "r"(k24), "r"(base));
-	return d;
-#else
-	(void)k24;
-	return base + (smem_addr_t)(ent >> 8);
-#endif
-}
-
 struct GatherLane {
 	smem_addr_t own;        // window of the lane's block: slot bank (sign copy with FOLD) + oy * pitch + ox + i0
 	smem_addr_t up;         // same for the block above (overlap lines only)
@@ -110,20 +96,18 @@ struct GatherLane {
 	int s_own, s_up;        // block signs (applied by multiplication when !FOLD)
 	int s_nb, s_nb_up;
 	bool word_aligned;      // own and up are multiples of 4: the lane's eight bytes of a slot row are two whole words
-	// The ALU pipe (LOP3, LEA, PRMT, the packed min/max) is the busier one (r02_gather_v2.md: ALU 66 %, FMA 17 %), so the two
-	// field extractions of a LUT entry = scale | slot offset << 8 are phrased as multiplies: with k24 = 2^24 (kept opaque),
-	// offset + base = mad.hi(entry, k24, base), and scale * 2^(16 - shift) = mul.hi(entry * k24, 2^(16 - shift) * 2^8).
-	uint32_t k24, pow16s8;
+	int pow16;
 	uint32_t lo2, hi2;
 };
 
 // Unfiltered grain (vertical overlap blended in, block sign applied) of sample E from its LUT entry: one byte gather
 // (two on an overlap line), bank conflicts as the windows and slots fall.
 template <bool FOLD, bool OVERLAP, int E>
-VFGS_HD int gather_sample(const GatherLane& L, uint32_t ent, smem_addr_t own_rc, smem_addr_t up_ru, int wc, int wu)
+VFGS_HD int gather_sample(const GatherLane& L, uint32_t ent, int rc, int ru, int wc, int wu)
 {
-	int g = lds_s8(entry_address(ent, L.k24, own_rc) + E);
-	if (OVERLAP) g = (g * wc + lds_s8(entry_address(ent, L.k24, up_ru) + E) * wu + 16) >> 5; // vfgs_hw.c:223-229; wc / wu carry the signs when !FOLD
+	const smem_addr_t off = (smem_addr_t)(ent >> 8) + E;
+	int g = lds_s8(L.own + rc + off);
+	if (OVERLAP) g = (g * wc + lds_s8(L.up + ru + off) * wu + 16) >> 5; // vfgs_hw.c:223-229; wc / wu carry the signs when !FOLD
 	else if (!FOLD) g *= L.s_own;
 	return g;
 }
@@ -136,7 +120,7 @@ VFGS_HD int octet_sample(const GatherLane& L, uint32_t c0, uint32_t c1, uint32_t
 	return g;
 }
 
-// One line of one lane, up to the exchange: g[] and sc[] (scale * 2^(16 - shift)). The eight LUT lookups come first. A lane whose eight samples all
+// One line of one lane, up to the exchange: g[] and sc[]. The eight LUT lookups come first. A lane whose eight samples all
 // select the same pattern slot (the rule on real pictures: the slot changes with the intensity INTERVAL,
 // vfgs_fw.c:598-622, and neighbouring samples mostly share one) and whose window is word aligned reads its eight
 // grain bytes as two consecutive words of that slot's row. The branch is per lane: in a mixed warp the hardware runs
@@ -156,8 +140,7 @@ VFGS_HD void gather_grain(const GatherLane& L, const uint32_t raw[4], int rc, in
 	ent[4] = lds32(L.lut | (smem_addr_t)index_bits<IN16, 4>(raw)); ent[5] = lds32(L.lut | (smem_addr_t)index_bits<IN16, 5>(raw));
 	ent[6] = lds32(L.lut | (smem_addr_t)index_bits<IN16, 6>(raw)); ent[7] = lds32(L.lut | (smem_addr_t)index_bits<IN16, 7>(raw));
 #pragma unroll
-	for (int e = 0; e < 8; e++) sc[e] = (int)mulhi_u32(ent[e] * L.k24, L.pow16s8); // scale * 2^(16 - shift)
-	const smem_addr_t own_rc = L.own + rc, up_ru = L.up + ru;
+	for (int e = 0; e < 8; e++) sc[e] = (int)(ent[e] & 0xffu);
 	if (VFGS_GATHER_OCTET_PATH) {
 		const uint32_t diff = ((ent[0] ^ ent[1]) | (ent[0] ^ ent[2]) | (ent[0] ^ ent[3])) | ((ent[0] ^ ent[4]) | (ent[0] ^ ent[5]) | (ent[0] ^ ent[6])) |
 		                      (ent[0] ^ ent[7]);
@@ -165,10 +148,10 @@ VFGS_HD void gather_grain(const GatherLane& L, const uint32_t raw[4], int rc, in
 #if !defined(__CUDA_ARCH__)
 			emu_warp().octet_lines++;
 #endif
-			const smem_addr_t a = entry_address(ent[0], L.k24, own_rc);
+			const smem_addr_t a = L.own + rc + (smem_addr_t)(ent[0] >> 8);
 			const uint32_t c0 = lds32(a), c1 = lds32(a + 4);
 			uint32_t u0 = 0, u1 = 0;
-			if (OVERLAP) { const smem_addr_t b = entry_address(ent[0], L.k24, up_ru); u0 = lds32(b); u1 = lds32(b + 4); }
+			if (OVERLAP) { const smem_addr_t b = L.up + ru + (smem_addr_t)(ent[0] >> 8); u0 = lds32(b); u1 = lds32(b + 4); }
 			g[0] = octet_sample<FOLD, OVERLAP, 0>(L, c0, c1, u0, u1, wc, wu); g[1] = octet_sample<FOLD, OVERLAP, 1>(L, c0, c1, u0, u1, wc, wu);
 			g[2] = octet_sample<FOLD, OVERLAP, 2>(L, c0, c1, u0, u1, wc, wu); g[3] = octet_sample<FOLD, OVERLAP, 3>(L, c0, c1, u0, u1, wc, wu);
 			g[4] = octet_sample<FOLD, OVERLAP, 4>(L, c0, c1, u0, u1, wc, wu); g[5] = octet_sample<FOLD, OVERLAP, 5>(L, c0, c1, u0, u1, wc, wu);
@@ -176,10 +159,10 @@ VFGS_HD void gather_grain(const GatherLane& L, const uint32_t raw[4], int rc, in
 			return;
 		}
 	}
-	g[0] = gather_sample<FOLD, OVERLAP, 0>(L, ent[0], own_rc, up_ru, wc, wu); g[1] = gather_sample<FOLD, OVERLAP, 1>(L, ent[1], own_rc, up_ru, wc, wu);
-	g[2] = gather_sample<FOLD, OVERLAP, 2>(L, ent[2], own_rc, up_ru, wc, wu); g[3] = gather_sample<FOLD, OVERLAP, 3>(L, ent[3], own_rc, up_ru, wc, wu);
-	g[4] = gather_sample<FOLD, OVERLAP, 4>(L, ent[4], own_rc, up_ru, wc, wu); g[5] = gather_sample<FOLD, OVERLAP, 5>(L, ent[5], own_rc, up_ru, wc, wu);
-	g[6] = gather_sample<FOLD, OVERLAP, 6>(L, ent[6], own_rc, up_ru, wc, wu); g[7] = gather_sample<FOLD, OVERLAP, 7>(L, ent[7], own_rc, up_ru, wc, wu);
+	g[0] = gather_sample<FOLD, OVERLAP, 0>(L, ent[0], rc, ru, wc, wu); g[1] = gather_sample<FOLD, OVERLAP, 1>(L, ent[1], rc, ru, wc, wu);
+	g[2] = gather_sample<FOLD, OVERLAP, 2>(L, ent[2], rc, ru, wc, wu); g[3] = gather_sample<FOLD, OVERLAP, 3>(L, ent[3], rc, ru, wc, wu);
+	g[4] = gather_sample<FOLD, OVERLAP, 4>(L, ent[4], rc, ru, wc, wu); g[5] = gather_sample<FOLD, OVERLAP, 5>(L, ent[5], rc, ru, wc, wu);
+	g[6] = gather_sample<FOLD, OVERLAP, 6>(L, ent[6], rc, ru, wc, wu); g[7] = gather_sample<FOLD, OVERLAP, 7>(L, ent[7], rc, ru, wc, wu);
 }
 
 // Unfiltered grain of the sample `v` next to a warp's end lane, from that sample's own intensity and its own block's
@@ -187,11 +170,11 @@ VFGS_HD void gather_grain(const GatherLane& L, const uint32_t raw[4], int rc, in
 template <bool FOLD, bool OVERLAP>
 VFGS_HD int gather_neighbour(const GatherLane& L, uint32_t v, int in_shift, int rc, int ru, int w_cur, int w_up)
 {
-	const uint32_t ent = lds32(L.lut | (smem_addr_t)(((v >> in_shift) & 0xffu) << 7));
-	int g = lds_s8(entry_address(ent, L.k24, L.nb + rc));
+	const smem_addr_t off = (smem_addr_t)(lds32(L.lut | (smem_addr_t)(((v >> in_shift) & 0xffu) << 7)) >> 8);
+	int g = lds_s8(L.nb + rc + off);
 	if (OVERLAP) {
 		const int wc = FOLD ? w_cur : w_cur * L.s_nb, wu = FOLD ? w_up : w_up * L.s_nb_up;
-		g = (g * wc + lds_s8(entry_address(ent, L.k24, L.nb_up + ru)) * wu + 16) >> 5;
+		g = (g * wc + lds_s8(L.nb_up + ru + off) * wu + 16) >> 5;
 	} else if (!FOLD) g *= L.s_nb;
 	return g;
 }
@@ -205,8 +188,8 @@ VFGS_HD void gather_finish(const GatherLane& L, const uint32_t raw[4], const int
 		uint32_t r[4];
 #pragma unroll
 		for (int k = 0; k < 4; k++) {
-			const int a_lo = sc[2 * k] * g[2 * k] + kRound;
-			const int a_hi = sc[2 * k + 1] * g[2 * k + 1] + kRound;
+			const int a_lo = (sc[2 * k] * L.pow16) * g[2 * k] + kRound;
+			const int a_hi = (sc[2 * k + 1] * L.pow16) * g[2 * k + 1] + kRound;
 			const uint32_t d2 = prmt((uint32_t)a_lo, (uint32_t)a_hi, 0x7632);
 			const uint32_t v2 = min_u16x2(raw[k], 0x3fff3fffu);
 			r[k] = min_s16x2(add_max_s16x2(v2, d2, L.lo2), L.hi2);
@@ -224,8 +207,8 @@ VFGS_HD void gather_finish(const GatherLane& L, const uint32_t raw[4], const int
 #pragma unroll
 		for (int k = 0; k < 4; k++) {
 			const uint32_t v2 = prmt(k < 2 ? raw[0] : raw[1], 0u, (k & 1) ? 0x4342 : 0x4140);
-			const int a_lo = sc[2 * k] * g[2 * k] + 0x8000;
-			const int a_hi = sc[2 * k + 1] * g[2 * k + 1] + 0x8000;
+			const int a_lo = (sc[2 * k] * L.pow16) * g[2 * k] + 0x8000;
+			const int a_hi = (sc[2 * k + 1] * L.pow16) * g[2 * k + 1] + 0x8000;
 			const uint32_t d2 = prmt((uint32_t)a_lo, (uint32_t)a_hi, 0x7632);
 			r[k] = min_s16x2(add_max_s16x2(v2, d2, L.lo2), L.hi2);
 		}
@@ -358,7 +341,7 @@ VFGS_HD void gather_task_body(const FgsParams& p, smem_addr_t luts, smem_addr_t 
 	const int stride = p.pat_stride[bank];
 	GatherLane L;
 	L.lut = luts + (smem_addr_t)(p.glut_index[c] * kLutBytes + lane * 4);
-	L.k24 = (uint32_t)p.k24; L.pow16s8 = (uint32_t)p.pow16 << 8;
+	L.pow16 = p.pow16;
 	constexpr int kOutBias = (IN16 && OUT8) ? 2 : 0;
 	L.lo2 = (uint32_t)(p.lo[c] + kOutBias) * 0x00010001u; L.hi2 = (uint32_t)(p.hi[c] + kOutBias) * 0x00010001u;
 

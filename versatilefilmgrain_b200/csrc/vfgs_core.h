@@ -163,7 +163,6 @@ struct FgsParams {
 	int in_bytes, out_bytes; // bytes per sample (1 | 2)
 	int bs, ss;             // depth - 8, effective scale shift
 	int pow16;              // 1 << (16 - ss), kept opaque so the kernels multiply (FMA pipe) instead of shifting (ALU pipe)
-	int k24;                // 1 << 24, opaque for the same reason (fgs_gather.h: LUT entry fields by multiplication)
 	int lo[3], hi[3];       // clip range per component, already << bs
 	int uniform_pi[3];      // pattern slot when the pattern LUT selects a single slot, else -1
 	int nseg[3], tasks_per_stripe;

@@ -173,7 +173,6 @@ inline void fill_state_params(FgsParams& p, const HwState& h, const TableInfo& b
 	p.subx = h.csubx; p.suby = h.csuby;
 	p.bs = h.bs; p.ss = h.scale_shift;
 	p.pow16 = 1 << (16 - h.scale_shift);
-	p.k24 = 1 << 24;
 	for (int c = 0; c < 3; c++) {
 		p.lo[c] = (c ? h.c_min : h.y_min) << h.bs;
 		p.hi[c] = (c ? h.c_max : h.y_max) << h.bs;

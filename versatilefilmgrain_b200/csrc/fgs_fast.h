@@ -301,12 +301,14 @@ VFGS_HD void st_piece2(uint8_t* p, uint32_t w)
 #endif
 }
 
+// The loaded pieces stay as they came until the line is used (edge_fix): combining them at load time would make the
+// lane wait for its loads right there instead of LB lines later. r[4] is only touched at the odd multiples of 2.
 template <int N>
-VFGS_HD void edge_load(const uint8_t* p, uint32_t r[4], int nv)
+VFGS_HD void edge_load(const uint8_t* p, uint32_t r[5], int nv)
 {
 	constexpr int SB = N / 8; // bytes per sample
-	r[0] = r[1] = r[2] = r[3] = 0;
-	if (nv < 8) { // samples right of the picture read as 0
+	if (nv < 8) { // partial last unit of a row, sample by sample; samples right of the picture read as 0 (one lane per row: it may wait)
+		r[0] = r[1] = r[2] = r[3] = 0;
 #pragma unroll
 		for (int e = 0; e < 8; e++) {
 			if (e < nv) {
@@ -322,20 +324,31 @@ VFGS_HD void edge_load(const uint8_t* p, uint32_t r[4], int nv)
 		if (a == 0) ld_piece16(p, r);
 		else if (a == 8) { ld_piece8(p, r); ld_piece8(p + 8, r + 2); }
 		else if ((a & 3) == 0) { r[0] = ld_piece4(p); ld_piece8(p + 4, r + 1); r[3] = ld_piece4(p + 12); }
-		else { // odd multiple of 2
-			const uint32_t h0 = ld_piece2(p), m0 = ld_piece4(p + 2), m1 = ld_piece4(p + 6), m2 = ld_piece4(p + 10), h1 = ld_piece2(p + 14);
-			r[0] = h0 | (m0 << 16); r[1] = prmt(m0, m1, 0x5432); r[2] = prmt(m1, m2, 0x5432); r[3] = (m2 >> 16) | (h1 << 16);
-		}
+		else { r[0] = ld_piece2(p); r[1] = ld_piece4(p + 2); r[2] = ld_piece4(p + 6); r[3] = ld_piece4(p + 10); r[4] = ld_piece2(p + 14); } // odd multiple of 2
 	} else {
 		if (a == 0) ld_piece8(p, r);
 		else if (a == 4) { r[0] = ld_piece4(p); r[1] = ld_piece4(p + 4); }
-		else if ((a & 1) == 0) {
-			const uint32_t h0 = ld_piece2(p), m = ld_piece4(p + 2), h1 = ld_piece2(p + 6);
-			r[0] = h0 | (m << 16); r[1] = (m >> 16) | (h1 << 16);
-		} else {
+		else if ((a & 1) == 0) { r[0] = ld_piece2(p); r[1] = ld_piece4(p + 2); r[2] = ld_piece2(p + 6); }
+		else { // odd addresses (8-bit samples, odd row pitch): bytes
+			r[0] = r[1] = 0;
 #pragma unroll
 			for (int e = 0; e < 8; e++) r[e >> 2] |= (uint32_t)p[e] << (8 * (e & 3));
 		}
+	}
+}
+// pieces -> the unit's words, for a unit loaded from address offset a (p & (N - 1)) with nv valid samples
+template <int N>
+VFGS_HD void edge_fix(uint32_t r[5], unsigned a, int nv)
+{
+	if (nv < 8) return;
+	if (N == 16) {
+		if ((a & 3) == 2) {
+			const uint32_t h0 = r[0], m0 = r[1], m1 = r[2], m2 = r[3], h1 = r[4];
+			r[0] = h0 | (m0 << 16); r[1] = prmt(m0, m1, 0x5432); r[2] = prmt(m1, m2, 0x5432); r[3] = (m2 >> 16) | (h1 << 16);
+		}
+	} else if ((a & 3) == 2) {
+		const uint32_t h0 = r[0], m = r[1], h1 = r[2];
+		r[0] = h0 | (m << 16); r[1] = (m >> 16) | (h1 << 16);
 	}
 }
 template <int N>
@@ -586,7 +599,7 @@ VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, const TaskGeom&
 	// The first LB lines are requested before anything else: the block decode below runs
 	// while they are in flight. A stripe shorter than LB lines re-reads its last line.
 	const int nv = EDGE ? (pl.width - k0 < kSamplesPerLane ? pl.width - k0 : kSamplesPerLane) : kSamplesPerLane; // valid samples of this unit
-	uint32_t raw[LB][4];
+	uint32_t raw[LB][EDGE ? 5 : 4];
 #pragma unroll
 	for (int q = 0; q < LB; q++) {
 		const int qq = q < nl ? q : nl - 1;
@@ -595,7 +608,7 @@ VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, const TaskGeom&
 		else ld_global_8(src + qq * in_pitch, raw[q]);
 	}
 
-	if (IN16 && PF > 0 && !EDGE) {
+	if (IN16 && PF > 0) {
 #pragma unroll
 		for (int q = LB; q < LB + PF; q++) prefetch_l1(src + q * in_pitch, q < nl);
 	}
@@ -644,13 +657,14 @@ VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, const TaskGeom&
 				int w_cur = 0, w_up = 0, ru = 0;
 				if (q == 0 && ovl) { w_cur = ysh ? 20 : 12; w_up = ysh ? 20 : 24; ru = (16 >> ysh) * L.stride; }
 				if (q == 1 && ovl && !ysh) { w_cur = 24; w_up = 12; ru = 17 * L.stride; }
+				if (EDGE) edge_fix<IN16 ? 16 : 8>(raw[q], (unsigned)((uintptr_t)(nxt - LB * in_pitch) & (IN16 ? 15 : 7)), nv);
 				fast_line<IN16, OUT8, NSH>(L, rc, w_cur, w_up, U, ru, raw[q], w);
 				// this slot's registers are free again: request the line LB further down
 				const bool refill = WHOLE ? more : line + LB < nl;
 				if (EDGE) { if (refill) edge_load<IN16 ? 16 : 8>(nxt, raw[q], nv); }
 				else if (IN16) ld_samples_16_if<kL1>(nxt, raw[q], refill);
 				else ld_global_8_if(nxt, raw[q], refill);
-				if (IN16 && PF > 0 && !EDGE) prefetch_l1(nxt + PF * in_pitch, line + LB + PF < nl);
+				if (IN16 && PF > 0) prefetch_l1(nxt + PF * in_pitch, line + LB + PF < nl);
 				if (WHOLE || line < nl) {
 					if (EDGE) edge_store<OB == 2 ? 16 : 8>(dst, w, nv);
 					else if (OB == 2) st_global_16(dst, w);

@@ -339,7 +339,7 @@ int launch_apply(const FgsParams& p, cudaStream_t stream, KernelKind kind = kGen
 		else
 			kern = p.in_bytes == 1 ? fgs_apply_fast_kernel<false, false, true>
 			     : p.out_bytes == 1 ? fgs_apply_fast_kernel<true, true, true> : fgs_apply_fast_kernel<true, false, true>;
-		threads = fast_threads(p.in_bytes == 2, p.in_bytes == 2 && p.out_bytes == 1); smem = p.fsmem;
+		threads = fast_threads(p.in_bytes == 2, p.in_bytes == 2 && p.out_bytes == 1, kind == kFastEdge); smem = p.fsmem;
 		if (smem > c.fast_smem_attr) {
 			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_fast_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_fast_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -150,16 +150,22 @@ fgs_apply_kernel(const __grid_constant__ FgsParams p)
 #ifndef VFGS_FAST_THREADS_IN8
 #define VFGS_FAST_THREADS_IN8 896   // 8-bit in, 8-bit out (2 bytes per sample: issue-bound; 73 registers keep the 16-samples-per-lane path free of spills)
 #endif
-template <bool IN16, bool OUT8> struct FastCta {
-	static constexpr int threads = !IN16 ? VFGS_FAST_THREADS_IN8 : OUT8 ? VFGS_FAST_THREADS8 : VFGS_FAST_THREADS16;
+#ifndef VFGS_FAST_THREADS_EDGE
+#define VFGS_FAST_THREADS_EDGE 768  // EDGE variants (ragged / unaligned rows): the piecewise accesses want the 85 registers of 24 warps
+#endif
+template <bool IN16, bool OUT8, bool EDGE = false> struct FastCta {
+	static constexpr int threads = EDGE ? VFGS_FAST_THREADS_EDGE : !IN16 ? VFGS_FAST_THREADS_IN8 : OUT8 ? VFGS_FAST_THREADS8 : VFGS_FAST_THREADS16;
 };
-inline int fast_threads(bool in16, bool out8) { return !in16 ? VFGS_FAST_THREADS_IN8 : out8 ? VFGS_FAST_THREADS8 : VFGS_FAST_THREADS16; }
+inline int fast_threads(bool in16, bool out8, bool edge = false)
+{
+	return edge ? VFGS_FAST_THREADS_EDGE : !in16 ? VFGS_FAST_THREADS_IN8 : out8 ? VFGS_FAST_THREADS8 : VFGS_FAST_THREADS16;
+}
 
 template <bool IN16, bool OUT8, bool EDGE = false>
-__global__ void __launch_bounds__(FastCta<IN16, OUT8>::threads, 1)
+__global__ void __launch_bounds__(FastCta<IN16, OUT8, EDGE>::threads, 1)
 fgs_apply_fast_kernel(const __grid_constant__ FgsParams p)
 {
-	constexpr int kFastThreads = FastCta<IN16, OUT8>::threads, kFastWarps = kFastThreads / 32;
+	constexpr int kFastThreads = FastCta<IN16, OUT8, EDGE>::threads, kFastWarps = kFastThreads / 32;
 	extern __shared__ __align__(128) uint8_t smem[];
 	__shared__ __align__(8) uint64_t bar;
 

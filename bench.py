@@ -467,37 +467,30 @@ def run_b200_arm(args):
         sustained = {"gbs": 2 * nbytes * reps / (cms * 1e-3) / 1e9, "seconds": cms * 1e-3, "what": "torch copy_ (cudaMemcpy D2D) of the input pool onto the output pool, read + write bytes",
                      "sm_mhz": ck["sm_mhz"], "reasons": ck["reasons"]}
 
-    # end to end through the host entry point: pinned host buffers, H2D + kernels + D2H timed
+    # ---- end to end through the host entry point: pinned host buffers, H2D + kernels + D2H timed -------------------
     Fe = min(F, args.e2e_frames or int(max(8, min(128, 2.4e9 // in_bytes))))
-    h_in = torch.empty(Fe * samples, dtype=src.dtype).pin_memory()
-    h_in.copy_(src[: Fe * samples])
-    h_out = torch.empty(Fe * samples, dtype=dst.dtype).pin_memory()
+    e2e_steps = max(3, min(args.steps, 20))
+    # The GPUs of one box do not sit behind equally fast host links (profiles/r02_pcie_matrix.json: with all eight busy,
+    # four of them get 8.5 GB/s each way, four 11.5), so with several ranks the step's world * Fe frames are dealt out in
+    # proportion to the copy rate every rank measures here, with all ranks copying at once: this step's H2D and D2H
+    # copies alone, concurrently on two streams from pinned buffers, no kernels. Summed over the ranks it is also the
+    # box's PCIe ceiling for the step (`pcie_copies_alone`).
+    cap = Fe if world == 1 else int(Fe * 1.5) + 1  # frames a rank may be dealt
+    h_in = torch.empty(cap * samples, dtype=src.dtype).pin_memory()
+    h_in[: Fe * samples].copy_(src[: Fe * samples])
+    if cap > Fe:
+        h_in[Fe * samples:].copy_(src[: (cap - Fe) * samples])
+    h_out = torch.empty(cap * samples, dtype=dst.dtype).pin_memory()
     del src, dst
     torch.cuda.empty_cache()
-    e2e_steps = max(3, min(args.steps, 20))
-    for s in range(2):
-        hw.add_grain_frames_host(h_in, h_out, Fe, w, h, od)
-    barrier()
-    t0 = time.perf_counter()
-    for s in range(e2e_steps):
-        hw.add_grain_frames_host(h_in, h_out, Fe, w, h, od)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * Fe * e2e_steps / float(t.item())
-
-    # the box's PCIe ceiling for the same bytes: this step's H2D and D2H copies alone, concurrently on two
-    # streams from the same pinned buffers, all ranks at once, no kernels
-    d_in, d_out = torch.empty_like(h_in, device="cuda"), torch.empty_like(h_out, device="cuda")
+    d_in, d_out = torch.empty(Fe * samples, dtype=h_in.dtype, device="cuda"), torch.empty(Fe * samples, dtype=h_out.dtype, device="cuda")
     s_up, s_down = torch.cuda.Stream(), torch.cuda.Stream()
 
     def copies():
         with torch.cuda.stream(s_up):
-            d_in.copy_(h_in, non_blocking=True)
+            d_in.copy_(h_in[: Fe * samples], non_blocking=True)
         with torch.cuda.stream(s_down):
-            h_out.copy_(d_out, non_blocking=True)
+            h_out[: Fe * samples].copy_(d_out, non_blocking=True)
 
     copies()
     barrier()
@@ -505,11 +498,36 @@ def run_b200_arm(args):
     for s in range(e2e_steps):
         copies()
     torch.cuda.synchronize()
-    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    my_copy_s = time.perf_counter() - t0
+    t = torch.tensor([my_copy_s], dtype=torch.float64, device="cuda")
+    rates = torch.zeros(world, dtype=torch.float64, device="cuda")
+    rates[rank] = Fe * e2e_steps / my_copy_s
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(rates, op=dist.ReduceOp.SUM)
     copy_only_value = world * Fe * e2e_steps / float(t.item())
     del d_in, d_out
+    from versatilefilmgrain_b200.sharding import weighted_shard_ranges
+    shards = weighted_shard_ranges(world * Fe, [min(float(r), 1.5 * float(rates.min().item())) for r in rates.tolist()]) if world > 1 else [(0, Fe)]
+    my_e2e_first, my_e2e = shards[rank]
+    my_e2e = min(my_e2e, cap)
+
+    def e2e_step(s):
+        position_shard(hw, epoch, s * world * Fe + my_e2e_first, w, h)
+        hw.add_grain_frames_host(h_in, h_out, my_e2e, w, h, od)
+
+    for s in range(2):
+        e2e_step(s)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(e2e_steps):
+        e2e_step(2 + s)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = sum(c for _, c in shards) * e2e_steps / float(t.item())
 
     peak, peak_src = measured_peak_gbs()
     # the grain kernels of one C-ABI call (one launch for single-pattern configs, two when components split between
@@ -537,8 +555,10 @@ def run_b200_arm(args):
         "pool_gb_per_gpu": F * (in_bytes + out_bytes) / 1e9,
         "timed_region_s": ms_max * 1e-3,
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": Fe * in_bytes, "d2h_bytes_per_step": Fe * out_bytes,
-                "frames_per_step": Fe, "steps": e2e_steps, "host_buffers": "pinned", "cpu_placement": placement, "scaling": "weak",
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": sum(c for _, c in shards) * in_bytes, "d2h_bytes_per_step": sum(c for _, c in shards) * out_bytes,
+                "frames_per_step": sum(c for _, c in shards), "frames_per_rank": [c for _, c in shards],
+                "shards": "one step = world x %d frames, dealt to the ranks in proportion to the copy rate each measured with all ranks copying" % Fe if world > 1 else "single rank",
+                "steps": e2e_steps, "host_buffers": "pinned", "cpu_placement": placement, "scaling": "weak",
                 "gbs_each_way": [e2e_value * in_bytes / 1e9, e2e_value * out_bytes / 1e9],
                 "pcie_copies_alone": {"value": copy_only_value, "unit": UNIT,
                                       "what": "the same H2D and D2H copies without kernels, concurrently, all ranks: the box's PCIe ceiling for this step"}},

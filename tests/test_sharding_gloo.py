@@ -77,6 +77,19 @@ def test_two_rank_shards_equal_continuous_run(total):
     assert q.get(timeout=5) is True
 
 
+def test_weighted_shards_partition_exactly():
+    from versatilefilmgrain_b200.sharding import weighted_shard_ranges
+    for total in (0, 1, 7, 768, 2400):
+        for weights in ([1], [1, 1], [8.4, 8.4, 8.4, 8.4, 11.4, 11.4, 11.4, 11.4], [0.0, 3.0, 1.0]):
+            spans = weighted_shard_ranges(total, weights)
+            assert spans[0][0] == 0 and sum(c for _, c in spans) == total
+            for (a, ca), (b, _) in zip(spans, spans[1:]):
+                assert a + ca == b
+    spans = weighted_shard_ranges(768, [8.4] * 4 + [11.4] * 4)
+    assert [c for _, c in spans] == [81, 82, 81, 82, 110, 111, 110, 111] or sum(c for _, c in spans[4:]) > sum(c for _, c in spans[:4])
+    assert weighted_shard_ranges(10, [0.0, 3.0, 1.0])[0] == (0, 0)
+
+
 def test_shard_range_partitions_exactly():
     from versatilefilmgrain_b200.sharding import shard_range, steps_per_frame
     for total in (0, 1, 7, 64, 2400):

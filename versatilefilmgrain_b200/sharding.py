@@ -20,6 +20,24 @@ def shard_range(total_frames: int, rank: int, world: int) -> tuple[int, int]:
     return first, count
 
 
+def weighted_shard_ranges(total_frames: int, weights) -> list[tuple[int, int]]:
+    """Contiguous shards whose sizes follow ``weights`` (e.g. the host<->device copy bandwidth each rank measured:
+    the GPUs of one box do not all sit behind equally fast links, profiles/r02_pcie_matrix.json). Largest-remainder
+    rounding; every rank's (first frame, frame count), in rank order, covering [0, total_frames) exactly."""
+    w = [max(float(x), 0.0) for x in weights]
+    if not w or total_frames < 0 or sum(w) <= 0:
+        raise ValueError("bad shard request")
+    exact = [total_frames * x / sum(w) for x in w]
+    counts = [int(e) for e in exact]
+    for i in sorted(range(len(w)), key=lambda i: exact[i] - counts[i], reverse=True)[: total_frames - sum(counts)]:
+        counts[i] += 1
+    out, first = [], 0
+    for c in counts:
+        out.append((first, c))
+        first += c
+    return out
+
+
 def steps_per_frame(width: int, height: int) -> int:
     """LFSR steps between the first block-rows of two consecutive frames: (R - 1) * nb. The first
     block-row of a frame re-uses the state of the previous frame's last block-row (vfgs_hw.c:291-298

@@ -176,6 +176,28 @@ def test_line_entry_point(hw, case):
     assert hw.get_lfsr() == o.get_lfsr()
 
 
+def test_wide_multi_pattern_line(hw):
+    """vfgs_add_grain_line on 4K-wide lines with 8 luma patterns: many warps and CTAs of the general kernel work on one
+    line, and every 256-sample segment boundary has a neighbour-sample read across it -- the line is staged out of
+    place on the device, so no warp can read what another has already written."""
+    case = "fgs_sei.cfg|d10|420|g100"
+    w, h = 4096, 36
+    frames = synth_frames(1, w, h, "420", 10, seed=77)
+    o = Oracle(); program_case(o, G, case)
+    exp = o.add_grain_frames(frames, 1, w, h, 0)
+    hw.reset(); program_case(hw, G, case)
+    work = frames.copy()
+    cw = w // 2
+    for rep in range(1):
+        for y in range(h):
+            Y = work[y * w:(y + 1) * w]
+            U = work[w * h + (y // 2) * cw: w * h + (y // 2 + 1) * cw]
+            V = work[w * h + cw * (h // 2) + (y // 2) * cw: w * h + cw * (h // 2) + (y // 2 + 1) * cw]
+            hw.vfgs_add_grain_line(Y, U, V, y, w)
+    assert np.array_equal(work, exp), first_mismatch(work, exp, w, h, "420", 1)
+    assert hw.get_lfsr() == o.get_lfsr()
+
+
 def test_split_calls_and_skip_frames_equal_one_call(hw):
     """Frame sharding property: [0,N) in one call == two consecutive calls == skip + second half."""
     case = "fgs_sei_ff_test6.cfg|d10|420|g100"

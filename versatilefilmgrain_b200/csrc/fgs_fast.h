@@ -428,38 +428,51 @@ VFGS_HD void edge_store(uint8_t* p, const uint32_t w[4], int nv)
 // multiple of 2), the result goes the other way: chunk l = the tail of unit l - 1 and the head of unit l, one aligned
 // 128-bit store per lane. Only the two ends of the warp's span are partial: lane 0 stores the head of its own unit,
 // lane 31 the tail of unit 30, sample by sample. A is a compile-time offset (the row offset is warp-uniform: a switch).
-// Branch-free on purpose: the row offset a changes from line to line, and a switch over its eight values in every
-// unrolled line of the loop made the loop body outgrow the instruction cache (profiles/r02_fast_edge_v2.md:
-// no_instruction 3.3 warps per issue cycle). The 8-word window {own chunk, next chunk} is shifted by a / 4 words with
-// two levels of selects and by the odd half-word with one byte permute per word whose selector is a register.
-VFGS_HD void window_words(const uint32_t X[9], unsigned word_shift, uint32_t half_sel, uint32_t out[4])
+template <int A>
+VFGS_HD void realign_in(const uint32_t c[4], int lane, uint32_t u[4])
 {
-	uint32_t Y[6], Z[5];
-#pragma unroll
-	for (int i = 0; i < 6; i++) Y[i] = (word_shift & 2u) ? X[i + 2] : X[i];
-#pragma unroll
-	for (int i = 0; i < 5; i++) Z[i] = (word_shift & 1u) ? Y[i + 1] : Y[i];
-#pragma unroll
-	for (int j = 0; j < 4; j++) out[j] = prmt(Z[j], Z[j + 1], half_sel);
-}
-// unit words from the lane's aligned chunk c and the next lane's: bytes [a, a + 16) of {c, next}
-VFGS_HD void realign_in_any(unsigned a, const uint32_t c[4], int lane, uint32_t u[4])
-{
+	constexpr int w = A >> 2, cnt = w + ((A & 3) ? 1 : 0);
 	uint32_t X[9] = {c[0], c[1], c[2], c[3], 0, 0, 0, 0, 0};
 #pragma unroll
-	for (int i = 0; i < 4; i++) X[4 + i] = (uint32_t)lane_exchange((int)c[i], lane + 1);
-	window_words(X, a >> 2, (a & 2u) ? 0x5432u : 0x3210u, u);
+	for (int i = 0; i < cnt; i++) X[4 + i] = (uint32_t)lane_exchange((int)c[i], lane + 1);
+#pragma unroll
+	for (int j = 0; j < 4; j++) u[j] = (A & 3) ? prmt(X[w + j], X[w + j + 1], 0x5432) : X[w + j];
 }
-// aligned chunk words from the previous lane's unit words and the lane's own o: bytes [16 - a, 32 - a) of {previous, o}
-VFGS_HD void realign_out_any(unsigned a, const uint32_t o[4], int lane, uint32_t ch[4])
+template <int A>
+VFGS_HD void realign_out(const uint32_t o[4], int lane, uint32_t ch[4])
 {
+	constexpr int k = (16 - A) >> 2; // the chunk starts at byte 16 - A = 4 k (+ 2) of {previous unit, own unit}
 	uint32_t X[9] = {0, 0, 0, 0, o[0], o[1], o[2], o[3], 0};
 #pragma unroll
-	for (int i = 0; i < 4; i++) X[i] = (uint32_t)lane_exchange((int)o[i], lane - 1);
-	const unsigned s = 16u - a; // 2 .. 16
-	window_words(X, (s >> 2) & 3u, (s & 2u) ? 0x5432u : 0x3210u, ch);
+	for (int i = k; i < 4; i++) X[i] = (uint32_t)lane_exchange((int)o[i], lane - 1);
 #pragma unroll
-	for (int j = 0; j < 4; j++) ch[j] = a ? ch[j] : o[j]; // a == 0: the chunk is the unit
+	for (int j = 0; j < 4; j++) ch[j] = (A & 3) ? prmt(X[k + j], X[k + j + 1], 0x5432) : X[k + j];
+}
+VFGS_HD void realign_in_any(unsigned a, const uint32_t c[4], int lane, uint32_t u[4])
+{
+	switch (a) {
+	case 0: u[0] = c[0]; u[1] = c[1]; u[2] = c[2]; u[3] = c[3]; break;
+	case 2: realign_in<2>(c, lane, u); break;
+	case 4: realign_in<4>(c, lane, u); break;
+	case 6: realign_in<6>(c, lane, u); break;
+	case 8: realign_in<8>(c, lane, u); break;
+	case 10: realign_in<10>(c, lane, u); break;
+	case 12: realign_in<12>(c, lane, u); break;
+	default: realign_in<14>(c, lane, u); break;
+	}
+}
+VFGS_HD void realign_out_any(unsigned a, const uint32_t o[4], int lane, uint32_t ch[4])
+{
+	switch (a) {
+	case 0: ch[0] = o[0]; ch[1] = o[1]; ch[2] = o[2]; ch[3] = o[3]; break;
+	case 2: realign_out<2>(o, lane, ch); break;
+	case 4: realign_out<4>(o, lane, ch); break;
+	case 6: realign_out<6>(o, lane, ch); break;
+	case 8: realign_out<8>(o, lane, ch); break;
+	case 10: realign_out<10>(o, lane, ch); break;
+	case 12: realign_out<12>(o, lane, ch); break;
+	default: realign_out<14>(o, lane, ch); break;
+	}
 }
 
 // Per-lane constants of a warp-task (pattern addresses have the block's sign folded in).
@@ -647,22 +660,17 @@ static_assert(kFastLB >= 2, "both vertical-overlap lines of a block-row must fal
 #endif
 
 // EDGE: rows at any sample-aligned address, partial last unit of a row (see edge_load / edge_store above)
-// RAL (EDGE only, 16-bit samples in and out, chosen per warp): the warp moves its bytes as aligned 128-bit chunks
-// (realign_in_any / realign_out_any) instead of piece by piece. The two forms are separate instantiations and the EDGE
-// bodies keep 2 lines in flight without the whole-group specialisation: with everything in one body unrolled four
-// times the loop outgrew the instruction cache (8,008 instructions against the plain kernel's 2,408).
-template <bool IN16, bool OUT8, int NSH, bool EDGE = false, bool RAL = false>
-VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, const TaskGeom& t, int k0, int lane)
+// realign (EDGE only, warp-uniform): the warp moves its bytes as aligned 128-bit chunks (realign_in / realign_out)
+template <bool IN16, bool OUT8, int NSH, bool EDGE = false>
+VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, const TaskGeom& t, int k0, int lane, bool realign = false)
 {
-	static_assert(!RAL || (EDGE && IN16 && !OUT8), "realigned accesses exist for the EDGE variant with 16-bit samples in and out");
-	constexpr bool RA = RAL;
-	constexpr bool realign = RAL;
+	constexpr bool RA = EDGE && IN16 && !OUT8; // realigned accesses exist for 16-bit samples in and out
 	const int c = t.c;
 	const smem_addr_t img = lut + (smem_addr_t)(ptrdiff_t)p.fimg_off[c]; // the component's pattern image
 	const Plane& pl = p.comp[c];
 	const int ysh = (c && p.suby > 1) ? 1 : 0;
 	constexpr int n = 1 << NSH;
-	constexpr int LB = EDGE ? 2 : OUT8 ? VFGS_FAST_LB8 : VFGS_FAST_LB16; // lines in flight per lane
+	constexpr int LB = OUT8 ? VFGS_FAST_LB8 : VFGS_FAST_LB16; // lines in flight per lane
 
 	// component lines of this stripe (whole stripes only: the host sends partial line ranges to
 	// the general kernel)
@@ -759,16 +767,10 @@ VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, const TaskGeom&
 					uint32_t ch[4];
 					realign_out_any(a_in, w, lane, ch);
 					if ((WHOLE || line < nl) && lane_stores()) {
-						if (lane >= 1 && lane <= 30) st_piece16(dst - a_in, ch);
-						else {
-							// the two ends of the warp's span, sample by sample: lane 0 stores the head of its own unit (all of it when a == 0),
-							// lane 31 the tail of unit 30 (nothing when a == 0)
-							const int count = lane == 0 ? (int)(16 - a_in) >> 1 : (int)a_in >> 1;
-							uint8_t* at = lane == 0 ? dst : dst - a_in;
-#pragma unroll
-							for (int e = 0; e < 8; e++)
-								if (e < count) st_piece2(at + 2 * e, (lane == 0 ? w[e >> 1] : ch[e >> 1]) >> (16 * (e & 1)));
-						}
+						if (a_in == 0) { if (lane < 31) st_piece16(dst, w); }
+						else if (lane >= 1 && lane <= 30) st_piece16(dst - a_in, ch);
+						else if (lane == 0) edge_store<16>(dst, w, (int)(16 - a_in) >> 1);        // head of the warp's span: own unit's first bytes
+						else edge_store<16>(dst - a_in, ch, (int)a_in >> 1);                        // tail: the last bytes of unit 30
 					}
 				} else if (WHOLE || line < nl) {
 					if (EDGE) { if (lane_stores()) edge_store<OB == 2 ? 16 : 8>(dst, w, nv); }
@@ -780,7 +782,7 @@ VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, const TaskGeom&
 			ovl = false;
 		}
 	};
-	if (!EDGE && nl % LB == 0) lines(std::true_type());
+	if (nl % LB == 0) lines(std::true_type());
 	else lines(std::false_type());
 }
 
@@ -940,19 +942,13 @@ VFGS_HD void process_task_fast(const FgsParams& p, smem_addr_t lut, uint32_t tas
 		const uint32_t row = fastdiv(q, p.div_funits[t.c]);
 		const int first = (int)(q - row * wpr) * 31;
 		const int width = p.comp[t.c].width;
-		const bool realign = EDGE && IN16 && !OUT8 && p.frealign[t.c] && (first + 32) * kSamplesPerLane <= width; // all 32 chunks inside the row
+		const bool realign = p.frealign[t.c] && (first + 32) * kSamplesPerLane <= width; // all 32 chunks inside the row
 		const int k0 = (first + lane) * kSamplesPerLane;
 		if (!realign && (lane == 31 || k0 >= width)) return;
 		t.r = p.row_begin + (int)row;
 		t.seg = 0;
-		constexpr bool kCanRealign = EDGE && IN16 && !OUT8;
-		if (kCanRealign && realign) {
-			if (t.c && p.subx > 1) fast_task_body<IN16, OUT8, 3, EDGE, kCanRealign>(p, lut, t, k0, lane);
-			else fast_task_body<IN16, OUT8, 4, EDGE, kCanRealign>(p, lut, t, k0, lane);
-		} else {
-			if (t.c && p.subx > 1) fast_task_body<IN16, OUT8, 3, EDGE>(p, lut, t, k0, lane);
-			else fast_task_body<IN16, OUT8, 4, EDGE>(p, lut, t, k0, lane);
-		}
+		if (t.c && p.subx > 1) fast_task_body<IN16, OUT8, 3, EDGE>(p, lut, t, k0, lane, realign);
+		else fast_task_body<IN16, OUT8, 4, EDGE>(p, lut, t, k0, lane, realign);
 		return;
 	}
 	const uint32_t unit = q * 32u + (uint32_t)lane;

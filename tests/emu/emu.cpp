@@ -23,33 +23,23 @@ struct StateDump { // == refh_state / oracle_dump
 	int scale_shift, bs, y_min, y_max, c_min, c_max, csubx, csuby;
 };
 
-// the EDGE variant's realigned accesses exchange words between lanes (warp shuffle on the device): like the gather task
-// code, every EDGE task runs several times until every exchanged value is right (fgs_fast.h, EmuWarp)
 template <bool IN16, bool OUT8, bool EDGE>
 void run_fast(const FgsParams& p, const uint8_t* lut)
 {
 	for (long long task = 0; task < p.total_tasks; task++)
-		for (int pass = EDGE ? 0 : 2; pass < 3; pass++) { // two chained exchanges (words in, words out): three passes
-			emu_warp().final_pass = pass == 2;
-			for (int lane = 0; lane < 32; lane++) {
-				emu_warp().lane = lane; emu_warp().point = 0;
-				process_task_fast<IN16, OUT8, EDGE>(p, smem_addr(lut), (uint32_t)task, lane);
-			}
-			emu_warp().cur ^= 1;
-		}
+		for (int lane = 0; lane < 32; lane++) process_task_fast<IN16, OUT8, EDGE>(p, smem_addr(lut), (uint32_t)task, lane);
 }
 
 // the gather task code exchanges grain values between lanes (warp shuffle on the device): every task runs twice,
-// the second time with the neighbours. values of the first (fgs_fast.h, EmuWarp)
+// first recording what each lane sends, then replaying with the neighbours' values (fgs_gather.h, EmuWarp)
 template <bool IN16, bool OUT8, bool FOLD, bool SHIFT>
 void run_gather(const FgsParams& p, const uint8_t* luts, const uint8_t* img)
 {
 	for (long long task = 0; task < p.total_tasks; task++)
 		for (int pass = 0; pass < 2; pass++) {
-			emu_warp().final_pass = pass == 1;
+			emu_warp().record = pass == 0;
 			for (int lane = 0; lane < 32; lane++)
 				process_task_gather<IN16, OUT8, FOLD, SHIFT>(p, smem_addr(luts), smem_addr(img), (uint32_t)task, lane);
-			emu_warp().cur ^= 1;
 		}
 }
 template <bool FOLD, bool SHIFT>

@@ -226,40 +226,6 @@ VFGS_HD void octet(smem_addr_t a, uint32_t& w0, uint32_t& w1)
 	else { w0 = lds32(a); w1 = lds32(a + 4); }
 }
 
-// ---- lane exchange -------------------------------------------------------------------------
-// Device: a warp shuffle. Host build (tests/emu runs the lanes one after the other): every task is run several times;
-// in each pass an exchange point hands out what the source lane sent at that point in the PREVIOUS pass and notes what
-// this lane sends now. After d + 1 passes every value that depends on a chain of d exchanges is right (gather task
-// code: d = 1; realigned EDGE accesses: d = 2, the stored words depend on the loaded ones); only the last pass stores.
-#if !defined(__CUDA_ARCH__)
-struct EmuWarp {
-	bool final_pass = true;
-	int lane = 0, point = 0, cur = 0;
-	long long octet_lines = 0; // lane-lines that took the uniform-slot octet path (tests/emu: is it really taken?)
-	int table[2][256][32];
-};
-inline EmuWarp& emu_warp() { static thread_local EmuWarp w; return w; }
-#endif
-VFGS_HD int lane_exchange(int v, int src_lane)
-{
-#if defined(__CUDA_ARCH__)
-	return __shfl_sync(0xffffffffu, v, src_lane);
-#else
-	EmuWarp& w = emu_warp();
-	const int pt = w.point++;
-	w.table[w.cur][pt][w.lane] = v;
-	return w.table[w.cur ^ 1][pt][src_lane & 31];
-#endif
-}
-VFGS_HD bool lane_stores()
-{
-#if defined(__CUDA_ARCH__)
-	return true;
-#else
-	return emu_warp().final_pass;
-#endif
-}
-
 // ---- rows at any address, ragged widths (EDGE variant) ---------------------------------------
 // The packed .yuv layout (src/yuv.c:162-214: stride = width) puts a row wherever the previous one ended: with a width
 // that is not a multiple of 8 samples (1366 x 768, the 964-sample chroma rows of 1928 x 1080) row starts cycle through
@@ -417,61 +383,6 @@ VFGS_HD void edge_store(uint8_t* p, const uint32_t w[4], int nv)
 #pragma unroll
 			for (int e = 0; e < 8; e++) p[e] = (uint8_t)(w[e >> 2] >> (8 * (e & 3)));
 		}
-	}
-}
-
-// ---- EDGE, realigned: whole 128-bit accesses for rows that start anywhere ----------------------------------
-// A warp that lies inside one row, 16-bit samples in and out, input and output rows at the same offset a from a 16-byte
-// boundary: its 32 lanes load the 32 ALIGNED 16-byte chunks that cover 31 lane units (unit l = the last 16 - a bytes
-// of chunk l and the first a bytes of chunk l + 1; lane 31 only contributes its chunk). A unit's words are assembled
-// from the lane's own chunk and the first words of the next lane's (warp shuffle, a funnel shift when a is an odd
-// multiple of 2), the result goes the other way: chunk l = the tail of unit l - 1 and the head of unit l, one aligned
-// 128-bit store per lane. Only the two ends of the warp's span are partial: lane 0 stores the head of its own unit,
-// lane 31 the tail of unit 30, sample by sample. A is a compile-time offset (the row offset is warp-uniform: a switch).
-template <int A>
-VFGS_HD void realign_in(const uint32_t c[4], int lane, uint32_t u[4])
-{
-	constexpr int w = A >> 2, cnt = w + ((A & 3) ? 1 : 0);
-	uint32_t X[9] = {c[0], c[1], c[2], c[3], 0, 0, 0, 0, 0};
-#pragma unroll
-	for (int i = 0; i < cnt; i++) X[4 + i] = (uint32_t)lane_exchange((int)c[i], lane + 1);
-#pragma unroll
-	for (int j = 0; j < 4; j++) u[j] = (A & 3) ? prmt(X[w + j], X[w + j + 1], 0x5432) : X[w + j];
-}
-template <int A>
-VFGS_HD void realign_out(const uint32_t o[4], int lane, uint32_t ch[4])
-{
-	constexpr int k = (16 - A) >> 2; // the chunk starts at byte 16 - A = 4 k (+ 2) of {previous unit, own unit}
-	uint32_t X[9] = {0, 0, 0, 0, o[0], o[1], o[2], o[3], 0};
-#pragma unroll
-	for (int i = k; i < 4; i++) X[i] = (uint32_t)lane_exchange((int)o[i], lane - 1);
-#pragma unroll
-	for (int j = 0; j < 4; j++) ch[j] = (A & 3) ? prmt(X[k + j], X[k + j + 1], 0x5432) : X[k + j];
-}
-VFGS_HD void realign_in_any(unsigned a, const uint32_t c[4], int lane, uint32_t u[4])
-{
-	switch (a) {
-	case 0: u[0] = c[0]; u[1] = c[1]; u[2] = c[2]; u[3] = c[3]; break;
-	case 2: realign_in<2>(c, lane, u); break;
-	case 4: realign_in<4>(c, lane, u); break;
-	case 6: realign_in<6>(c, lane, u); break;
-	case 8: realign_in<8>(c, lane, u); break;
-	case 10: realign_in<10>(c, lane, u); break;
-	case 12: realign_in<12>(c, lane, u); break;
-	default: realign_in<14>(c, lane, u); break;
-	}
-}
-VFGS_HD void realign_out_any(unsigned a, const uint32_t o[4], int lane, uint32_t ch[4])
-{
-	switch (a) {
-	case 0: ch[0] = o[0]; ch[1] = o[1]; ch[2] = o[2]; ch[3] = o[3]; break;
-	case 2: realign_out<2>(o, lane, ch); break;
-	case 4: realign_out<4>(o, lane, ch); break;
-	case 6: realign_out<6>(o, lane, ch); break;
-	case 8: realign_out<8>(o, lane, ch); break;
-	case 10: realign_out<10>(o, lane, ch); break;
-	case 12: realign_out<12>(o, lane, ch); break;
-	default: realign_out<14>(o, lane, ch); break;
 	}
 }
 
@@ -660,11 +571,9 @@ static_assert(kFastLB >= 2, "both vertical-overlap lines of a block-row must fal
 #endif
 
 // EDGE: rows at any sample-aligned address, partial last unit of a row (see edge_load / edge_store above)
-// realign (EDGE only, warp-uniform): the warp moves its bytes as aligned 128-bit chunks (realign_in / realign_out)
 template <bool IN16, bool OUT8, int NSH, bool EDGE = false>
-VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, const TaskGeom& t, int k0, int lane, bool realign = false)
+VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, const TaskGeom& t, int k0, int lane)
 {
-	constexpr bool RA = EDGE && IN16 && !OUT8; // realigned accesses exist for 16-bit samples in and out
 	const int c = t.c;
 	const smem_addr_t img = lut + (smem_addr_t)(ptrdiff_t)p.fimg_off[c]; // the component's pattern image
 	const Plane& pl = p.comp[c];
@@ -694,8 +603,7 @@ VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, const TaskGeom&
 #pragma unroll
 	for (int q = 0; q < LB; q++) {
 		const int qq = q < nl ? q : nl - 1;
-		if (RA && realign) ld_piece16(src + qq * in_pitch - ((uintptr_t)(src + qq * in_pitch) & 15), raw[q]);
-		else if (EDGE) edge_load<IN16 ? 16 : 8>(src + qq * in_pitch, raw[q], nv);
+		if (EDGE) edge_load<IN16 ? 16 : 8>(src + qq * in_pitch, raw[q], nv);
 		else if (IN16) ld_samples_16<kL1>(src + qq * in_pitch, raw[q]);
 		else ld_global_8(src + qq * in_pitch, raw[q]);
 	}
@@ -749,31 +657,16 @@ VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, const TaskGeom&
 				int w_cur = 0, w_up = 0, ru = 0;
 				if (q == 0 && ovl) { w_cur = ysh ? 20 : 12; w_up = ysh ? 20 : 24; ru = (16 >> ysh) * L.stride; }
 				if (q == 1 && ovl && !ysh) { w_cur = 24; w_up = 12; ru = 17 * L.stride; }
-				const unsigned a_in = EDGE ? (unsigned)((uintptr_t)(nxt - LB * in_pitch) & (IN16 ? 15 : 7)) : 0u;
-				if (RA && realign) {
-					uint32_t unit[4];
-					realign_in_any(a_in, raw[q], lane, unit);
-					raw[q][0] = unit[0]; raw[q][1] = unit[1]; raw[q][2] = unit[2]; raw[q][3] = unit[3];
-				} else if (EDGE) edge_fix<IN16 ? 16 : 8>(raw[q], a_in, nv);
+				if (EDGE) edge_fix<IN16 ? 16 : 8>(raw[q], (unsigned)((uintptr_t)(nxt - LB * in_pitch) & (IN16 ? 15 : 7)), nv);
 				fast_line<IN16, OUT8, NSH>(L, rc, w_cur, w_up, U, ru, raw[q], w);
 				// this slot's registers are free again: request the line LB further down
 				const bool refill = WHOLE ? more : line + LB < nl;
-				if (RA && realign) { if (refill) ld_piece16(nxt - ((uintptr_t)nxt & 15), raw[q]); }
-				else if (EDGE) { if (refill) edge_load<IN16 ? 16 : 8>(nxt, raw[q], nv); }
+				if (EDGE) { if (refill) edge_load<IN16 ? 16 : 8>(nxt, raw[q], nv); }
 				else if (IN16) ld_samples_16_if<kL1>(nxt, raw[q], refill);
 				else ld_global_8_if(nxt, raw[q], refill);
 				if (IN16 && PF > 0) prefetch_l1(nxt + PF * in_pitch, line + LB + PF < nl);
-				if (RA && realign) { // input and output rows share the offset (the host checked): a_in is the store offset too
-					uint32_t ch[4];
-					realign_out_any(a_in, w, lane, ch);
-					if ((WHOLE || line < nl) && lane_stores()) {
-						if (a_in == 0) { if (lane < 31) st_piece16(dst, w); }
-						else if (lane >= 1 && lane <= 30) st_piece16(dst - a_in, ch);
-						else if (lane == 0) edge_store<16>(dst, w, (int)(16 - a_in) >> 1);        // head of the warp's span: own unit's first bytes
-						else edge_store<16>(dst - a_in, ch, (int)a_in >> 1);                        // tail: the last bytes of unit 30
-					}
-				} else if (WHOLE || line < nl) {
-					if (EDGE) { if (lane_stores()) edge_store<OB == 2 ? 16 : 8>(dst, w, nv); }
+				if (WHOLE || line < nl) {
+					if (EDGE) edge_store<OB == 2 ? 16 : 8>(dst, w, nv);
 					else if (OB == 2) st_global_16(dst, w);
 					else st_global_8(dst, w);
 				}
@@ -934,23 +827,6 @@ VFGS_HD void process_task_fast(const FgsParams& p, smem_addr_t lut, uint32_t tas
 	t.c = 0;
 	if (q >= (uint32_t)p.ftasks[0]) { q -= (uint32_t)p.ftasks[0]; t.c = 1; }
 	if (t.c == 1 && q >= (uint32_t)p.ftasks[1]) { q -= (uint32_t)p.ftasks[1]; t.c = 2; }
-	if (EDGE) {
-		// EDGE launches: a warp-task lies inside one row and holds 31 lane units (lane 31 only lends its 16-byte chunk to the
-		// realigned accesses); funits_per_row counts the warps of a row
-		const uint32_t wpr = (uint32_t)p.funits_per_row[t.c];
-		if (q >= wpr * (uint32_t)p.rows) return;
-		const uint32_t row = fastdiv(q, p.div_funits[t.c]);
-		const int first = (int)(q - row * wpr) * 31;
-		const int width = p.comp[t.c].width;
-		const bool realign = p.frealign[t.c] && (first + 32) * kSamplesPerLane <= width; // all 32 chunks inside the row
-		const int k0 = (first + lane) * kSamplesPerLane;
-		if (!realign && (lane == 31 || k0 >= width)) return;
-		t.r = p.row_begin + (int)row;
-		t.seg = 0;
-		if (t.c && p.subx > 1) fast_task_body<IN16, OUT8, 3, EDGE>(p, lut, t, k0, lane, realign);
-		else fast_task_body<IN16, OUT8, 4, EDGE>(p, lut, t, k0, lane, realign);
-		return;
-	}
 	const uint32_t unit = q * 32u + (uint32_t)lane;
 	const uint32_t upr = (uint32_t)p.funits_per_row[t.c];
 	if (unit >= upr * (uint32_t)p.rows) return;

@@ -26,7 +26,7 @@
 //     copies fit into shared memory, else the sign is applied by one multiply per sample).
 //   * The two (one) vertical-overlap lines of a stripe are peeled off the steady-state line loop.
 // Restates vfgs_hw.c:140-284 per sample like fgs_task.h; host-compilable for tests/emu (the host build replays
-// the shuffles from a table, see EmuWarp in fgs_fast.h).
+// the shuffles from a table, see EmuWarp).
 #pragma once
 #include "fgs_fast.h"
 
@@ -40,6 +40,39 @@ namespace vfgs {
 #endif
 constexpr int kGatherLB = VFGS_GATHER_LB; // lines in flight per lane
 static_assert(kGatherLB >= 2, "both vertical-overlap lines of a block-row must fall into the first group of lines");
+
+// ---- lane exchange -------------------------------------------------------------------------
+// Device: a warp shuffle. Host build (tests/emu runs the lanes one after the other): every task is run twice,
+// a recording pass that only notes what each lane sends at each exchange point, and a replaying pass that reads
+// the neighbours' values from that table and is the only one that stores.
+#if !defined(__CUDA_ARCH__)
+struct EmuWarp {
+	bool record = false;
+	int lane = 0, point = 0;
+	long long octet_lines = 0; // lane-lines that took the uniform-slot octet path (tests/emu: is it really taken?)
+	int table[64][32];
+};
+inline EmuWarp& emu_warp() { static thread_local EmuWarp w; return w; }
+#endif
+VFGS_HD int lane_exchange(int v, int src_lane)
+{
+#if defined(__CUDA_ARCH__)
+	return __shfl_sync(0xffffffffu, v, src_lane);
+#else
+	EmuWarp& w = emu_warp();
+	const int pt = w.point++;
+	if (w.record) { w.table[pt][w.lane] = v; return 0; }
+	return w.table[pt][src_lane & 31];
+#endif
+}
+VFGS_HD bool lane_stores()
+{
+#if defined(__CUDA_ARCH__)
+	return true;
+#else
+	return !emu_warp().record;
+#endif
+}
 
 // LUT index bits (intensity * 128) of sample e of a lane's raw words.
 template <bool IN16, int E>
@@ -113,7 +146,7 @@ VFGS_HD void gather_grain(const GatherLane& L, const uint32_t raw[4], int rc, in
 		                      (ent[0] ^ ent[7]);
 		if ((diff >> 8) == 0 && L.word_aligned) {
 #if !defined(__CUDA_ARCH__)
-			if (emu_warp().final_pass) emu_warp().octet_lines++;
+			emu_warp().octet_lines++;
 #endif
 			const smem_addr_t a = L.own + rc + (smem_addr_t)(ent[0] >> 8);
 			const uint32_t c0 = lds32(a), c1 = lds32(a + 4);

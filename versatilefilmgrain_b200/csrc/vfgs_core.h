@@ -171,7 +171,6 @@ struct FgsParams {
 	// (units_per_row * rows of them per frame), cut into warp-tasks of 32 units regardless of row ends
 	int funits_per_row[3], ftasks[3], ftasks_per_frame;
 	int fwide[3];           // 8-bit input: the component's lane units are 16 samples (fgs_fast.h, wide_task_body)
-	int frealign[3];        // EDGE launch: input and output rows of the component share their offset from a 16-byte boundary (realigned accesses)
 	FastDiv div_funits[3], div_ftasks;
 	// table image ("blob") copied to shared memory by every CTA
 	const uint8_t* blob;

@@ -320,17 +320,6 @@ inline void plan_launches(const FgsParams& p, const TableInfo& bi, int mode, boo
 			             aligned_for(f.comp[c].out, f.comp[c].out_row_bytes, f.out_frame_bytes, 16);
 			f.funits_per_row[c] = kind[c] == k ? (f.comp[c].width + (f.fwide[c] ? 16 : kSamplesPerLane) - 1) / (f.fwide[c] ? 16 : kSamplesPerLane) : 0;
 			f.ftasks[c] = (f.funits_per_row[c] * f.rows + 31) / 32;
-			f.frealign[c] = 0;
-			if (k == 3 && kind[c] == 3) { // EDGE: warps of 31 units inside one row (process_task_fast); funits_per_row = warps per row
-				f.funits_per_row[c] = (f.funits_per_row[c] + 30) / 31;
-				f.ftasks[c] = f.funits_per_row[c] * f.rows;
-				const long long d = (long long)((uintptr_t)f.comp[c].in & 15) - (long long)((uintptr_t)f.comp[c].out & 15);
-				f.frealign[c] = f.in_bytes == 2 && f.out_bytes == 2 && d == 0 && (f.comp[c].in_row_bytes - f.comp[c].out_row_bytes) % 16 == 0 &&
-				                (f.in_frame_bytes - f.out_frame_bytes) % 16 == 0;
-#ifdef VFGS_EDGE_NO_REALIGN
-				f.frealign[c] = 0; // build-time knob for experiments
-#endif
-			}
 			f.ftasks_per_frame += f.ftasks[c];
 			f.div_funits[c] = make_fastdiv((uint32_t)(f.funits_per_row[c] > 0 ? f.funits_per_row[c] : 1));
 		}

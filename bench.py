@@ -469,13 +469,15 @@ def run_b200_arm(args):
 
     # ---- end to end through the host entry point: pinned host buffers, H2D + kernels + D2H timed -------------------
     Fe = min(F, args.e2e_frames or int(max(8, min(128, 2.4e9 // in_bytes))))
+    if world > 1 and not args.e2e_frames:
+        Fe = max(8, Fe * 2 // 3)  # several ranks pin their buffers on one host: keep the total below what one rank used to take times N
     e2e_steps = max(3, min(args.steps, 20))
     # The GPUs of one box do not sit behind equally fast host links (profiles/r02_pcie_matrix.json: with all eight busy,
     # four of them get 8.5 GB/s each way, four 11.5), so with several ranks the step's world * Fe frames are dealt out in
     # proportion to the copy rate every rank measures here, with all ranks copying at once: this step's H2D and D2H
     # copies alone, concurrently on two streams from pinned buffers, no kernels. Summed over the ranks it is also the
     # box's PCIe ceiling for the step (`pcie_copies_alone`).
-    cap = Fe if world == 1 else int(Fe * 1.5) + 1  # frames a rank may be dealt
+    cap = Fe if world == 1 else int(Fe * 1.35) + 1  # frames a rank may be dealt
     h_in = torch.empty(cap * samples, dtype=src.dtype).pin_memory()
     h_in[: Fe * samples].copy_(src[: Fe * samples])
     if cap > Fe:
@@ -508,7 +510,7 @@ def run_b200_arm(args):
     copy_only_value = world * Fe * e2e_steps / float(t.item())
     del d_in, d_out
     from versatilefilmgrain_b200.sharding import weighted_shard_ranges
-    shards = weighted_shard_ranges(world * Fe, [min(float(r), 1.5 * float(rates.min().item())) for r in rates.tolist()]) if world > 1 else [(0, Fe)]
+    shards = weighted_shard_ranges(world * Fe, [min(float(r), 1.35 * float(rates.min().item())) for r in rates.tolist()]) if world > 1 else [(0, Fe)]
     my_e2e_first, my_e2e = shards[rank]
     my_e2e = min(my_e2e, cap)
 

@@ -125,7 +125,7 @@ VFGS_HD int octet_sample(const GatherLane& L, uint32_t c0, uint32_t c1, uint32_t
 // vfgs_fw.c:598-622, and neighbouring samples mostly share one) and whose window is word aligned reads its eight
 // grain bytes as two consecutive words of that slot's row. The branch is per lane: in a mixed warp the hardware runs
 // both sides one after the other, each with its own lanes only, and a byte gather issued for a handful of lanes
-// hardly conflicts, so the shared-memory wavefronts (the kernel's bound: profiles/r02_gather_v2.md) shrink with every
+// hardly conflicts, so the shared-memory wavefronts (the kernel's bound: profiles/r02_gather_uniform.md) shrink with every
 // lane that qualifies. Uniformly random samples never qualify and pay five extra instructions per line for the test.
 #ifndef VFGS_GATHER_OCTET_PATH
 #define VFGS_GATHER_OCTET_PATH 1 // build-time knob for experiments
@@ -245,10 +245,10 @@ VFGS_HD uint32_t ld_sample_if(const uint8_t* p, bool pred)
 #endif
 }
 // The kernel keeps few lines in flight per lane (registers: LB = 2 at 28 warps = 28 KB per SM) and was bound by the
-// latency of its line loads once the instruction count had come down (long_scoreboard 4.9 warps per issue cycle,
-// profiles/r02_gather_v2.md). Lines further down the stripe are therefore prefetched into L1 (no registers), and the line
-// loads are ordinary cached loads that find them there. Measured on B200 (profiles/r02_gather_ab.md, same box):
-// natural data 0.753 -> 0.835 of the HBM peak, uniform 0.742 -> 0.775 with 4 lines of prefetch.
+// latency of its line loads once the instruction count had come down (long_scoreboard 4.9 warps per issue cycle before,
+// 1.4 after: profiles/r02_gather_natural.md). Lines further down the stripe are therefore prefetched into L1 (no registers),
+// and the line loads are ordinary cached loads that find them there. Measured on B200 (profiles/r02_gather_ab.md, same
+// box, two rounds): smooth pictures 0.747 -> 0.791 of the HBM peak, uniform random samples 0.724 -> 0.741.
 #ifndef VFGS_GATHER_PREFETCH
 #define VFGS_GATHER_PREFETCH 4 // lines ahead of the line loads that are prefetched into L1 (0: none, line loads bypass L1)
 #endif

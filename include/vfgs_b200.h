@@ -53,9 +53,11 @@ const char* vfgs_b200_last_error(void);
 size_t vfgs_b200_frame_bytes(int width, int height, int depth);
 
 /* nframes packed planar frames already in DEVICE memory; asynchronous on `stream` (a cudaStream_t,
- * NULL = default stream). in == out is allowed when the depths match (with sample-adaptive pattern
- * selection the frames then take a detour through a scratch buffer: two extra passes over the data);
- * otherwise the buffers must not overlap. */
+ * NULL = default stream). in == out (every plane identical, same strides) is allowed when the depths
+ * match: the kernels then read nothing but what they overwrite themselves; only components with
+ * sample-adaptive pattern selection AND 8-sample blocks or ragged / unaligned rows take a detour through a
+ * scratch buffer (two extra passes over the data). Input and output that overlap in any other way are
+ * refused with VFGS_B200_ERR_ARG. */
 int vfgs_b200_add_grain_frames_device(const void* in, void* out, int nframes, int width, int height,
                                       int out_depth, void* stream);
 
@@ -99,9 +101,10 @@ uint64_t vfgs_b200_launch_count(void);
 int vfgs_b200_kernel_timing(int enable);
 int vfgs_b200_kernel_time(double* total_ms, uint64_t* launches);
 
-/* Test aid: kernel selection. 0 = automatic (fast kernel for single-pattern components, gather kernel
- * for sample-adaptive ones, general kernel for ragged/unaligned layouts), 1 = general kernel for
- * everything, 2 = gather kernel wherever it can run. All three are CUDA paths. */
+/* Test aid: kernel selection. 0 = automatic (fast kernel for single-pattern components -- its EDGE variant
+ * for ragged / unaligned rows --, gather kernel for sample-adaptive ones, general kernel for sample-adaptive
+ * components on ragged / unaligned rows), 1 = general kernel for everything, 2 = gather kernel wherever it
+ * can run. All of them are CUDA paths. */
 void vfgs_b200_force_general_kernel(int mode);
 
 /* Frame pipeline behind include/yuv.h: out[0] = frames processed, out[1] = batches flushed. */
@@ -109,7 +112,7 @@ void vfgs_b200_pipeline_stats(unsigned long long out[2]);
 
 /* Geometry of the last grain kernel launch: out[0]=grid, out[1]=block, out[2]=dynamic smem bytes,
  * out[3]=SM count of the bound device, out[4]=which grain kernels the last frame call launched
- * (bit 0 fast, bit 1 general, bit 2 gather). */
+ * (bit 0 fast, bit 1 general, bit 2 gather, bit 3 the fast kernel's EDGE variant). */
 void vfgs_b200_last_launch(int out[5]);
 
 #ifdef __cplusplus

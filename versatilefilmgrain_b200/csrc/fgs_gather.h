@@ -252,9 +252,7 @@ VFGS_HD uint32_t ld_sample_if(const uint8_t* p, bool pred)
 #ifndef VFGS_GATHER_PREFETCH
 #define VFGS_GATHER_PREFETCH 4 // lines ahead of the line loads that are prefetched into L1 (0: none, line loads bypass L1)
 #endif
-#ifndef VFGS_GATHER_XPREFETCH
-#define VFGS_GATHER_XPREFETCH 0 // lines of the warp's NEXT task prefetched while the current one ends (build-time knob for experiments)
-#endif
+// (Prefetching the first lines of the warp's NEXT task as well was measured without gain and removed, profiles/r02_gather_ab.md.)
 // line loads of the gather kernel: cached (they hit the prefetched lines) unless prefetching is off
 template <bool IN16>
 VFGS_HD void gather_ld_if(const uint8_t* p, uint32_t r[4], bool pred)
@@ -282,7 +280,7 @@ VFGS_HD void gather_ld_if(const uint8_t* p, uint32_t r[4], bool pred)
 // Every lane walks the full line count of a stripe (the exchange is a warp-wide shuffle); lanes outside the picture
 // or past the end of a short last stripe neither load nor store.
 template <bool IN16, bool OUT8, int NSH, bool FOLD, bool SHIFT>
-VFGS_HD void gather_task_body(const FgsParams& p, smem_addr_t luts, smem_addr_t img, int f, int c, uint32_t q, int lane, uint32_t next_q)
+VFGS_HD void gather_task_body(const FgsParams& p, smem_addr_t luts, smem_addr_t img, int f, int c, uint32_t q, int lane)
 {
 	constexpr bool PAIR = NSH == 4;
 	static_assert(PAIR || !SHIFT, "the shifted numbering exists for 16-sample blocks only");
@@ -417,40 +415,26 @@ VFGS_HD void gather_task_body(const FgsParams& p, smem_addr_t luts, smem_addr_t 
 		}
 	};
 	group(0, std::true_type());
-	if (VFGS_GATHER_XPREFETCH > 0 && next_q) { // the first lines of this warp's next task (same component and frame), while this one runs
-		const long long u2 = (long long)next_q * 32 + lane - (SHIFT ? 1 : 0);
-		if (u2 < (long long)upr * (uint32_t)p.rows) {
-			const uint32_t row2 = fastdiv((uint32_t)u2, p.div_gunits[c]);
-			const int k2 = (int)((uint32_t)u2 - row2 * upr) * kSamplesPerLane;
-			const int cl2 = ((p.row_begin + (int)row2) * 16) >> ysh;
-			const uint8_t* s2 = pl.in + (long long)f * p.in_frame_bytes + (long long)cl2 * in_pitch + (long long)k2 * IB;
-#pragma unroll
-			for (int qq = 0; qq < VFGS_GATHER_XPREFETCH; qq++) prefetch_l1(s2 + qq * in_pitch, k2 < pl.width && cl2 + qq < pl.lines);
-		}
-	}
 #pragma unroll 1
 	for (int base = LB; base < lines; base += LB) group(base, std::false_type());
 }
 
 // Gather-kernel task numbering: per frame the gather components one after the other, each cut into warp-tasks of
 // 32 consecutive flat units.
-// task_stride: distance to the same warp's next task (0: unknown, no cross-task prefetch)
 template <bool IN16, bool OUT8, bool FOLD, bool SHIFT>
-VFGS_HD void process_task_gather(const FgsParams& p, smem_addr_t luts, smem_addr_t img, uint32_t task, int lane, uint32_t task_stride = 0)
+VFGS_HD void process_task_gather(const FgsParams& p, smem_addr_t luts, smem_addr_t img, uint32_t task, int lane)
 {
 	const int f = (int)fastdiv(task, p.div_gtasks);
 	uint32_t q = task - (uint32_t)f * (uint32_t)p.gtasks_per_frame;
 	int c = 0;
 	if (q >= (uint32_t)p.gtasks[0]) { q -= (uint32_t)p.gtasks[0]; c = 1; }
 	if (c == 1 && q >= (uint32_t)p.gtasks[1]) { q -= (uint32_t)p.gtasks[1]; c = 2; }
-	// the next task of this warp, when it lies in the same component of the same frame (else 0)
-	const uint32_t next_q = (task_stride && q + task_stride < (uint32_t)p.gtasks[c]) ? q + task_stride : 0u;
 #if !defined(__CUDA_ARCH__)
 	emu_warp().lane = lane; emu_warp().point = 0;
 #endif
-	if (SHIFT) gather_task_body<IN16, OUT8, 4, FOLD, true>(p, luts, img, f, c, q, lane, next_q); // the host never sends 8-sample blocks here
-	else if (c && p.subx > 1) gather_task_body<IN16, OUT8, 3, FOLD, false>(p, luts, img, f, c, q, lane, next_q);
-	else gather_task_body<IN16, OUT8, 4, FOLD, false>(p, luts, img, f, c, q, lane, next_q);
+	if (SHIFT) gather_task_body<IN16, OUT8, 4, FOLD, true>(p, luts, img, f, c, q, lane); // the host never sends 8-sample blocks here
+	else if (c && p.subx > 1) gather_task_body<IN16, OUT8, 3, FOLD, false>(p, luts, img, f, c, q, lane);
+	else gather_task_body<IN16, OUT8, 4, FOLD, false>(p, luts, img, f, c, q, lane);
 }
 
 } // namespace vfgs

@@ -243,7 +243,7 @@ fgs_apply_gather_kernel(const __grid_constant__ FgsParams p)
 	const smem_addr_t luts = smem_addr(lut_ptr), img = smem_addr(img_ptr);
 	const long long stride = (long long)gridDim.x * kGatherWarps;
 	for (long long task = (long long)blockIdx.x * kGatherWarps + (threadIdx.x >> 5); task < p.total_tasks; task += stride)
-		process_task_gather<IN16, OUT8, FOLD, SHIFT>(p, luts, img, (uint32_t)task, lane, (uint32_t)stride);
+		process_task_gather<IN16, OUT8, FOLD, SHIFT>(p, luts, img, (uint32_t)task, lane);
 }
 
 // ---- firmware layer: one pattern job (fw_device.h) -----------------------------------------------

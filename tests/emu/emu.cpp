@@ -168,10 +168,8 @@ extern "C" int emu_add_grain_frames(const void* state, const void* in, void* out
 			const uint16_t* compact = (const uint16_t*)(gi + g.lut_off) + c * 256;
 			uint32_t* lut = (uint32_t*)(gl + (size_t)g.glut_index[c] * kLutBytes);
 			const uint32_t slot_bytes = (uint32_t)g.pat_size[c ? 1 : 0];
-			for (int i = 0; i < 256 * 32; i++) {
-				const uint32_t e = compact[i >> 5];
-				lut[i] = (e & 0xffu) | (((e >> 8) * slot_bytes) << 8);
-			}
+			for (int i = 0; i < 256 * 32; i++)
+				lut[i] = isz == 2 ? gather_lut_entry<true>(compact[i >> 5], slot_bytes) : gather_lut_entry<false>(compact[i >> 5], slot_bytes);
 		}
 		if (lp.gather_fold) { if (lp.gather_shift) run_gather_any<true, true>(g, isz, osz, gl, gi); else run_gather_any<true, false>(g, isz, osz, gl, gi); }
 		else { if (lp.gather_shift) run_gather_any<false, true>(g, isz, osz, gl, gi); else run_gather_any<false, false>(g, isz, osz, gl, gi); }

@@ -51,6 +51,9 @@ VFGS_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
 // sign-extended byte e (0..7) of the octet {w1,w0}. FMA_TOP: the top byte of each word comes out of a multiply-high
 // (arithmetic shift by 24 on the FMA pipe): the ALU pipe is the busier one in the issue-bound variants (8-bit output
 // or input: +0.3 / +5 points measured); the HBM-bound 16-bit variant loses 2 points with it and keeps the PRMT.
+#ifndef VFGS_OCTET_TOP_ON_FMA
+#define VFGS_OCTET_TOP_ON_FMA 1 // build-time knob for experiments
+#endif
 template <int E, bool FMA_TOP = false>
 VFGS_HD int octet_byte(uint32_t w0, uint32_t w1)
 {
@@ -114,6 +117,17 @@ VFGS_HD uint32_t mulhi_u32(uint32_t a, uint32_t b)
 #else
 	return (uint32_t)(((uint64_t)a * b) >> 32);
 #endif
+}
+// a >> N. Round 1 did this by a high multiply to move work from the ALU pipe to the FMA pipe; measured again in round 2
+// under the sustained protocol the plain shift wins on every kernel (IMAD.HI is the expensive one of the two:
+// profiles/r02_gather_ab.md, "LUT entry layout and shifts"), so the multiply is only a build-time knob now.
+#ifndef VFGS_SHR_ON_FMA
+#define VFGS_SHR_ON_FMA 0
+#endif
+template <int N>
+VFGS_HD uint32_t shr_fma(uint32_t a)
+{
+	return VFGS_SHR_ON_FMA ? mulhi_u32(a, 1u << (32 - N)) : a >> N;
 }
 
 // ---- shared-memory image of the fast path --------------------------------------------------
@@ -427,7 +441,7 @@ VFGS_HD void scale_add_clip_8bit(smem_addr_t lut, uint32_t lo2, uint32_t hi2, co
 	for (int k = 0; k < 4; k++) {
 		const uint32_t v2 = prmt(k < 2 ? raw0 : raw1, 0u, (k & 1) ? 0x4342 : 0x4140);
 		const int s_lo = (int)lds32(lut | (smem_addr_t)((v2 << 7) & 0x7f80u));
-		const int s_hi = (int)lds32(lut | (smem_addr_t)(mulhi_u32(v2, 1u << 23) & 0x7f80u)); // v2 >> 9 on the FMA pipe
+		const int s_hi = (int)lds32(lut | (smem_addr_t)(shr_fma<9>(v2) & 0x7f80u));
 		const int a_lo = s_lo * g[2 * k] + 0x8000;
 		const int a_hi = s_hi * g[2 * k + 1] + 0x8000;
 		const uint32_t d2 = prmt((uint32_t)a_lo, (uint32_t)a_hi, 0x7632);
@@ -448,7 +462,7 @@ VFGS_HD void fast_line(const FastLane& L, int rc, int w_cur, int w_up, const Fas
 	uint32_t c0, c1;
 	octet(L.own + rc, c0, c1);
 	int g[8];
-	constexpr bool kFmaTop = OUT8 || !IN16;
+	constexpr bool kFmaTop = VFGS_OCTET_TOP_ON_FMA && (OUT8 || !IN16);
 	g[0] = octet_byte<0>(c0, c1); g[1] = octet_byte<1>(c0, c1); g[2] = octet_byte<2>(c0, c1); g[3] = octet_byte<3, kFmaTop>(c0, c1);
 	g[4] = octet_byte<4>(c0, c1); g[5] = octet_byte<5>(c0, c1); g[6] = octet_byte<6>(c0, c1); g[7] = octet_byte<7, kFmaTop>(c0, c1);
 	if (MergeHalo<IN16, OUT8>::value && NSH == 4) {
@@ -499,7 +513,7 @@ VFGS_HD void fast_line(const FastLane& L, int rc, int w_cur, int w_up, const Fas
 		for (int k = 0; k < 4; k++) {
 			// LUT index = (sample >> 2) & 0xff (vfgs_hw.c:211), times the 128-byte LUT row pitch
 			const int s_lo = (int)lds32(L.lut | (smem_addr_t)((raw[k] << 5) & 0x7f80u));
-			const int s_hi = (int)lds32(L.lut | (smem_addr_t)(mulhi_u32(raw[k], 1u << 21) & 0x7f80u)); // raw >> 11 on the FMA pipe
+			const int s_hi = (int)lds32(L.lut | (smem_addr_t)(shr_fma<11>(raw[k]) & 0x7f80u));
 			const int a_lo = s_lo * g[2 * k] + kRound;
 			const int a_hi = s_hi * g[2 * k + 1] + kRound;
 			const uint32_t d2 = prmt((uint32_t)a_lo, (uint32_t)a_hi, 0x7632);
@@ -698,8 +712,8 @@ struct WideUp {
 
 VFGS_HD void octet_to_ints(uint32_t w0, uint32_t w1, int g[8])
 {
-	g[0] = octet_byte<0>(w0, w1); g[1] = octet_byte<1>(w0, w1); g[2] = octet_byte<2>(w0, w1); g[3] = octet_byte<3, true>(w0, w1);
-	g[4] = octet_byte<4>(w0, w1); g[5] = octet_byte<5>(w0, w1); g[6] = octet_byte<6>(w0, w1); g[7] = octet_byte<7, true>(w0, w1);
+	g[0] = octet_byte<0>(w0, w1); g[1] = octet_byte<1>(w0, w1); g[2] = octet_byte<2>(w0, w1); g[3] = octet_byte<3, VFGS_OCTET_TOP_ON_FMA != 0>(w0, w1);
+	g[4] = octet_byte<4>(w0, w1); g[5] = octet_byte<5>(w0, w1); g[6] = octet_byte<6>(w0, w1); g[7] = octet_byte<7, VFGS_OCTET_TOP_ON_FMA != 0>(w0, w1);
 }
 VFGS_HD void blend_octet(int g[8], uint32_t u0, uint32_t u1, int w_cur, int w_up)
 {

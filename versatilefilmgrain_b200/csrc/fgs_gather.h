@@ -4,7 +4,7 @@
 // (fgs_fast.h: lane = 8 samples, lines in flight with rotating refill, packed 16-bit clip), but the
 // grain byte of every sample is a true gather:
 //     entry = lut[intensity]            one conflict-free 32-bit shared load; the component has its own
-//                                       per-lane replicated table, entry = scale | slot byte offset << 8
+//                                       per-lane replicated table, entry = scale + slot (layouts: gather_lut_entry)
 //     grain = pattern[slot offset + window row + column]      one byte load, bank conflicts as they fall
 // Second version (round 2). What changed against the first one, and why (profiles/r01_v13_fgs_apply_gather.md:
 // 20 lane-instructions per sample, 45 shared-memory wavefronts per 256 samples, 53 % of them replays):
@@ -80,7 +80,7 @@ VFGS_HD uint32_t index_bits(const uint32_t raw[4])
 {
 	if (IN16) {
 		const uint32_t w = raw[E >> 1];
-		return (E & 1) ? (mulhi_u32(w, 1u << 21) & 0x7f80u) : ((w << 5) & 0x7f80u); // ((v >> 2) & 0xff) << 7
+		return (E & 1) ? (shr_fma<11>(w) & 0x7f80u) : ((w << 5) & 0x7f80u); // ((v >> 2) & 0xff) << 7
 	} else {
 		const uint32_t w = raw[E >> 2];
 		constexpr int sh = (E & 3) * 8;
@@ -97,15 +97,42 @@ struct GatherLane {
 	int s_nb, s_nb_up;
 	bool word_aligned;      // own and up are multiples of 4: the lane's eight bytes of a slot row are two whole words
 	int pow16;
+	uint32_t slot_mul;      // TOP layout: bytes per slot
 	uint32_t lo2, hi2;
 };
 
+// Layouts of a LUT entry (expanded from the table image's compact `scale | slot << 8` when a CTA starts).
+//   TOP (10-bit input): scale | slot << 27. Both uses of the entry then take it WHOLE, without masking out the other
+//     field: entry * pow16 = scale << (16 - ss) exactly, because the slot field leaves the 32-bit word (43 - ss >= 32:
+//     ss = scale_shift <= 11 whenever the input is 10 bits deep, the library's entry check ss + bs <= 13 restating
+//     vfgs_hw.c:170), and the slot's byte offset is (entry >> 27) * slot bytes (a shift and a multiply on the FMA pipe).
+//     That is eight ALU-pipe instructions less per eight samples on a kernel whose ALU pipe is its busiest unit on
+//     real pictures (profiles/r02_gather_natural.md).
+//   else (8-bit input, ss up to 13): scale | slot byte offset << 8.
+template <bool TOP>
+VFGS_HD uint32_t gather_lut_entry(uint32_t compact, uint32_t slot_bytes)
+{
+	return TOP ? (compact & 0xffu) | ((compact >> 8) << 27) : (compact & 0xffu) | (((compact >> 8) * slot_bytes) << 8);
+}
+template <bool TOP>
+VFGS_HD smem_addr_t entry_slot_offset(const GatherLane& L, uint32_t ent)
+{
+	return (smem_addr_t)(TOP ? (ent >> 27) * L.slot_mul : ent >> 8);
+}
+// scale << (16 - scale_shift)
+template <bool TOP>
+VFGS_HD int entry_scale16(const GatherLane& L, uint32_t ent)
+{
+	return (int)((TOP ? ent : ent & 0xffu) * (uint32_t)L.pow16);
+}
+template <bool TOP> struct EntrySlot { static constexpr uint32_t lsb = TOP ? 1u << 27 : 1u << 8; }; // lowest bit of the slot field
+
 // Unfiltered grain (vertical overlap blended in, block sign applied) of sample E from its LUT entry: one byte gather
 // (two on an overlap line), bank conflicts as the windows and slots fall.
-template <bool FOLD, bool OVERLAP, int E>
+template <bool TOP, bool FOLD, bool OVERLAP, int E>
 VFGS_HD int gather_sample(const GatherLane& L, uint32_t ent, int rc, int ru, int wc, int wu)
 {
-	const smem_addr_t off = (smem_addr_t)(ent >> 8) + E;
+	const smem_addr_t off = entry_slot_offset<TOP>(L, ent) + E;
 	int g = lds_s8(L.own + rc + off);
 	if (OVERLAP) g = (g * wc + lds_s8(L.up + ru + off) * wu + 16) >> 5; // vfgs_hw.c:223-229; wc / wu carry the signs when !FOLD
 	else if (!FOLD) g *= L.s_own;
@@ -140,18 +167,19 @@ VFGS_HD void gather_grain(const GatherLane& L, const uint32_t raw[4], int rc, in
 	ent[4] = lds32(L.lut | (smem_addr_t)index_bits<IN16, 4>(raw)); ent[5] = lds32(L.lut | (smem_addr_t)index_bits<IN16, 5>(raw));
 	ent[6] = lds32(L.lut | (smem_addr_t)index_bits<IN16, 6>(raw)); ent[7] = lds32(L.lut | (smem_addr_t)index_bits<IN16, 7>(raw));
 #pragma unroll
-	for (int e = 0; e < 8; e++) sc[e] = (int)(ent[e] & 0xffu);
+	for (int e = 0; e < 8; e++) sc[e] = entry_scale16<IN16>(L, ent[e]);
 	if (VFGS_GATHER_OCTET_PATH) {
 		const uint32_t diff = ((ent[0] ^ ent[1]) | (ent[0] ^ ent[2]) | (ent[0] ^ ent[3])) | ((ent[0] ^ ent[4]) | (ent[0] ^ ent[5]) | (ent[0] ^ ent[6])) |
 		                      (ent[0] ^ ent[7]);
-		if ((diff >> 8) == 0 && L.word_aligned) {
+		if (diff < EntrySlot<IN16>::lsb && L.word_aligned) {
 #if !defined(__CUDA_ARCH__)
 			emu_warp().octet_lines++;
 #endif
-			const smem_addr_t a = L.own + rc + (smem_addr_t)(ent[0] >> 8);
+			const smem_addr_t so = entry_slot_offset<IN16>(L, ent[0]);
+			const smem_addr_t a = L.own + rc + so;
 			const uint32_t c0 = lds32(a), c1 = lds32(a + 4);
 			uint32_t u0 = 0, u1 = 0;
-			if (OVERLAP) { const smem_addr_t b = L.up + ru + (smem_addr_t)(ent[0] >> 8); u0 = lds32(b); u1 = lds32(b + 4); }
+			if (OVERLAP) { const smem_addr_t b = L.up + ru + so; u0 = lds32(b); u1 = lds32(b + 4); }
 			g[0] = octet_sample<FOLD, OVERLAP, 0>(L, c0, c1, u0, u1, wc, wu); g[1] = octet_sample<FOLD, OVERLAP, 1>(L, c0, c1, u0, u1, wc, wu);
 			g[2] = octet_sample<FOLD, OVERLAP, 2>(L, c0, c1, u0, u1, wc, wu); g[3] = octet_sample<FOLD, OVERLAP, 3>(L, c0, c1, u0, u1, wc, wu);
 			g[4] = octet_sample<FOLD, OVERLAP, 4>(L, c0, c1, u0, u1, wc, wu); g[5] = octet_sample<FOLD, OVERLAP, 5>(L, c0, c1, u0, u1, wc, wu);
@@ -159,18 +187,18 @@ VFGS_HD void gather_grain(const GatherLane& L, const uint32_t raw[4], int rc, in
 			return;
 		}
 	}
-	g[0] = gather_sample<FOLD, OVERLAP, 0>(L, ent[0], rc, ru, wc, wu); g[1] = gather_sample<FOLD, OVERLAP, 1>(L, ent[1], rc, ru, wc, wu);
-	g[2] = gather_sample<FOLD, OVERLAP, 2>(L, ent[2], rc, ru, wc, wu); g[3] = gather_sample<FOLD, OVERLAP, 3>(L, ent[3], rc, ru, wc, wu);
-	g[4] = gather_sample<FOLD, OVERLAP, 4>(L, ent[4], rc, ru, wc, wu); g[5] = gather_sample<FOLD, OVERLAP, 5>(L, ent[5], rc, ru, wc, wu);
-	g[6] = gather_sample<FOLD, OVERLAP, 6>(L, ent[6], rc, ru, wc, wu); g[7] = gather_sample<FOLD, OVERLAP, 7>(L, ent[7], rc, ru, wc, wu);
+	g[0] = gather_sample<IN16, FOLD, OVERLAP, 0>(L, ent[0], rc, ru, wc, wu); g[1] = gather_sample<IN16, FOLD, OVERLAP, 1>(L, ent[1], rc, ru, wc, wu);
+	g[2] = gather_sample<IN16, FOLD, OVERLAP, 2>(L, ent[2], rc, ru, wc, wu); g[3] = gather_sample<IN16, FOLD, OVERLAP, 3>(L, ent[3], rc, ru, wc, wu);
+	g[4] = gather_sample<IN16, FOLD, OVERLAP, 4>(L, ent[4], rc, ru, wc, wu); g[5] = gather_sample<IN16, FOLD, OVERLAP, 5>(L, ent[5], rc, ru, wc, wu);
+	g[6] = gather_sample<IN16, FOLD, OVERLAP, 6>(L, ent[6], rc, ru, wc, wu); g[7] = gather_sample<IN16, FOLD, OVERLAP, 7>(L, ent[7], rc, ru, wc, wu);
 }
 
 // Unfiltered grain of the sample `v` next to a warp's end lane, from that sample's own intensity and its own block's
 // window (the value the neighbouring warp's end lane computes for itself).
-template <bool FOLD, bool OVERLAP>
+template <bool TOP, bool FOLD, bool OVERLAP>
 VFGS_HD int gather_neighbour(const GatherLane& L, uint32_t v, int in_shift, int rc, int ru, int w_cur, int w_up)
 {
-	const smem_addr_t off = (smem_addr_t)(lds32(L.lut | (smem_addr_t)(((v >> in_shift) & 0xffu) << 7)) >> 8);
+	const smem_addr_t off = entry_slot_offset<TOP>(L, lds32(L.lut | (smem_addr_t)(((v >> in_shift) & 0xffu) << 7)));
 	int g = lds_s8(L.nb + rc + off);
 	if (OVERLAP) {
 		const int wc = FOLD ? w_cur : w_cur * L.s_nb, wu = FOLD ? w_up : w_up * L.s_nb_up;
@@ -179,7 +207,7 @@ VFGS_HD int gather_neighbour(const GatherLane& L, uint32_t v, int in_shift, int 
 	return g;
 }
 
-// scale, add, clip (vfgs_hw.c:239, 260-267) and the optional 10 -> 8 bit conversion (yuv.c:231)
+// scale, add, clip (vfgs_hw.c:239, 260-267) and the optional 10 -> 8 bit conversion (yuv.c:231); sc[] = scale << (16 - scale_shift)
 template <bool IN16, bool OUT8>
 VFGS_HD void gather_finish(const GatherLane& L, const uint32_t raw[4], const int g[8], const int sc[8], uint32_t outw[4])
 {
@@ -188,8 +216,8 @@ VFGS_HD void gather_finish(const GatherLane& L, const uint32_t raw[4], const int
 		uint32_t r[4];
 #pragma unroll
 		for (int k = 0; k < 4; k++) {
-			const int a_lo = (sc[2 * k] * L.pow16) * g[2 * k] + kRound;
-			const int a_hi = (sc[2 * k + 1] * L.pow16) * g[2 * k + 1] + kRound;
+			const int a_lo = sc[2 * k] * g[2 * k] + kRound;
+			const int a_hi = sc[2 * k + 1] * g[2 * k + 1] + kRound;
 			const uint32_t d2 = prmt((uint32_t)a_lo, (uint32_t)a_hi, 0x7632);
 			const uint32_t v2 = min_u16x2(raw[k], 0x3fff3fffu);
 			r[k] = min_s16x2(add_max_s16x2(v2, d2, L.lo2), L.hi2);
@@ -207,8 +235,8 @@ VFGS_HD void gather_finish(const GatherLane& L, const uint32_t raw[4], const int
 #pragma unroll
 		for (int k = 0; k < 4; k++) {
 			const uint32_t v2 = prmt(k < 2 ? raw[0] : raw[1], 0u, (k & 1) ? 0x4342 : 0x4140);
-			const int a_lo = (sc[2 * k] * L.pow16) * g[2 * k] + 0x8000;
-			const int a_hi = (sc[2 * k + 1] * L.pow16) * g[2 * k + 1] + 0x8000;
+			const int a_lo = sc[2 * k] * g[2 * k] + 0x8000;
+			const int a_hi = sc[2 * k + 1] * g[2 * k + 1] + 0x8000;
 			const uint32_t d2 = prmt((uint32_t)a_lo, (uint32_t)a_hi, 0x7632);
 			r[k] = min_s16x2(add_max_s16x2(v2, d2, L.lo2), L.hi2);
 		}
@@ -340,6 +368,7 @@ VFGS_HD void gather_task_body(const FgsParams& p, smem_addr_t luts, smem_addr_t 
 	GatherLane L;
 	L.lut = luts + (smem_addr_t)(p.glut_index[c] * kLutBytes + lane * 4);
 	L.pow16 = p.pow16;
+	L.slot_mul = p.gslot_mul[c ? 1 : 0];
 	constexpr int kOutBias = (IN16 && OUT8) ? 2 : 0;
 	L.lo2 = (uint32_t)(p.lo[c] + kOutBias) * 0x00010001u; L.hi2 = (uint32_t)(p.hi[c] + kOutBias) * 0x00010001u;
 
@@ -376,13 +405,13 @@ VFGS_HD void gather_task_body(const FgsParams& p, smem_addr_t luts, smem_addr_t 
 					const int w_c = qq == 0 ? (ysh ? 20 : 12) : 24, w_u = qq == 0 ? (ysh ? 20 : 24) : 12;
 					const int ru = ((16 + qq) >> ysh) * stride;
 					gather_grain<IN16, FOLD, true>(L, raw[qq], rc, ru, w_c, w_u, g, sc);
-					if (!SHIFT) gh = gather_neighbour<FOLD, true>(L, vh[qq], p.bs, rc, ru, w_c, w_u);
+					if (!SHIFT) gh = gather_neighbour<IN16, FOLD, true>(L, vh[qq], p.bs, rc, ru, w_c, w_u);
 					done = true;
 				}
 			}
 			if (!done) {
 				gather_grain<IN16, FOLD, false>(L, raw[qq], rc, 0, 0, 0, g, sc);
-				if (!SHIFT) gh = gather_neighbour<FOLD, false>(L, vh[qq], p.bs, rc, 0, 0, 0);
+				if (!SHIFT) gh = gather_neighbour<IN16, FOLD, false>(L, vh[qq], p.bs, rc, 0, 0, 0);
 			}
 
 			// block-edge filter (vfgs_hw.c:250-259): both sides read the unfiltered grain of the other side

@@ -197,6 +197,7 @@ struct FgsParams {
 	// the general image and (sign-folded launches) the distance from a bank's slots to their negated copies
 	int glut_index[3], ngather;
 	int gpat_off[2], gneg_off[2];
+	uint32_t gslot_mul[2];  // bytes per slot of each bank (fgs_gather.h, TOP layout)
 	// gather kernel task numbering: a component's stripes are one flat run of 8-sample lane units, rows padded to an
 	// even number of units; a warp-task holds 32 (16-sample blocks) or 30 (8-sample blocks) consecutive units
 	int gunits_per_row[3], gtasks[3], gtasks_per_frame;

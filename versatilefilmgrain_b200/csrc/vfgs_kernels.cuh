@@ -199,7 +199,7 @@ fgs_apply_fast_kernel(const __grid_constant__ FgsParams p)
 }
 
 // Gather path: components with sample-adaptive pattern selection (fgs_gather.h). Shared memory: one
-// per-lane replicated LUT (32 KB, entry = scale | slot byte offset << 8) per gather component, each on a
+// per-lane replicated LUT (32 KB, entry layouts: gather_lut_entry) per gather component, each on a
 // 32 KB boundary, then the general table image (compact LUTs + pattern slots; FOLD: + the negated slots)
 // brought in by one bulk copy.
 #ifndef VFGS_GATHER_THREADS
@@ -233,8 +233,7 @@ fgs_apply_gather_kernel(const __grid_constant__ FgsParams p)
 		uint32_t* lut = (uint32_t*)(lut_ptr + p.glut_index[c] * kLutBytes);
 		const uint32_t slot_bytes = (uint32_t)p.pat_size[c ? 1 : 0];
 		for (int i = threadIdx.x; i < 256 * 32; i += kGatherThreads) {
-			const uint32_t e = compact[i >> 5];
-			lut[i] = (e & 0xffu) | (((e >> 8) * slot_bytes) << 8);
+			lut[i] = gather_lut_entry<IN16>(compact[i >> 5], slot_bytes);
 		}
 	}
 	__syncthreads();

@@ -329,6 +329,7 @@ inline void plan_launches(const FgsParams& p, const TableInfo& bi, int mode, boo
 	lp.gather.ngather = ngather;
 	lp.gather.gpat_off[0] = bi.pat_off[0]; lp.gather.gpat_off[1] = bi.pat_off[1];
 	lp.gather.gneg_off[0] = bi.neg_off[0]; lp.gather.gneg_off[1] = bi.neg_off[1];
+	lp.gather.gslot_mul[0] = (uint32_t)bi.pat_size[0]; lp.gather.gslot_mul[1] = (uint32_t)bi.pat_size[1];
 	lp.gather.blob_bytes = lp.gather_fold ? bi.gbytes : bi.bytes;
 	{ // the gather kernel numbers its tasks over flat runs of lane units as well (gather_task_body)
 		FgsParams& g = lp.gather;

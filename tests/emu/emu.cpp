@@ -177,7 +177,8 @@ extern "C" int emu_add_grain_frames(const void* state, const void* in, void* out
 	if (lp.any_general)
 		for (long long task = 0; task < lp.general.total_tasks; task++)
 			for (int lane = 0; lane < 32; lane++) process_task(lp.general, tab, (uint32_t)task, lane);
-	return (lp.any_fast ? 1 : 0) | (lp.any_general ? 2 : 0) | (lp.any_gather ? 4 : 0) | (lp.any_gather && lp.gather_fold ? 8 : 0) | (lp.any_gather && lp.gather_shift ? 16 : 0) | (lp.any_edge ? 32 : 0);
+	return (lp.any_fast ? 1 : 0) | (lp.any_general ? 2 : 0) | (lp.any_gather ? 4 : 0) | (lp.any_gather && lp.gather_fold ? 8 : 0) | (lp.any_gather && lp.gather_shift ? 16 : 0) | (lp.any_edge ? 32 : 0) |
+	       (lp.any_fast && (lp.fast.fwide[0] || lp.fast.fwide[1] || lp.fast.fwide[2]) ? 64 : 0);
 }
 
 // Launch planning of a whole-frame call, without running anything (host logic only): which kernel serves each

@@ -21,16 +21,30 @@ def emu():
     return L
 
 
-def run_emu(emu, o: Oracle, frames, n, w, h, od, first=0, mode=0):
-    """mode: 0 automatic, 1 general task code only, 2 gather task code wherever possible.
+WIDE = 64  # mask bit: some component of the fast launch ran 16 samples per lane
+
+
+def aligned_empty(n, dtype, offset=0):
+    """n elements whose first byte sits `offset` bytes after a 64-byte boundary (numpy itself only promises 16)."""
+    item = np.dtype(dtype).itemsize
+    raw = np.zeros(n * item + 128, dtype=np.uint8)
+    start = (-raw.ctypes.data) % 64 + offset
+    return raw[start:start + n * item].view(dtype)
+
+
+def run_emu(emu, o: Oracle, frames, n, w, h, od, first=0, mode=0, offset=0, full_mask=False):
+    """mode: 0 automatic, 1 general task code only, 2 gather task code wherever possible. The buffers start `offset`
+    bytes after a 64-byte boundary (the 16-samples-per-lane paths need 16 / 32-byte aligned rows).
     Returns (output, mask): mask bit 0 = fast, bit 1 = general, bit 2 = gather task code ran, bit 3 = the gather
-    code read sign-folded slot copies."""
+    code read sign-folded slot copies, bit 4 = shifted gather numbering, bit 5 = EDGE variant; with full_mask also
+    bit 6 = WIDE."""
     st = RefState()
     o.L.oracle_get_state(o.h, C.byref(st))
     depth = 8 + st.bs
-    out = np.zeros(frames.shape, dtype=np.uint8 if (od == 8 or depth == 8) else np.uint16)
-    mask = emu.emu_add_grain_frames(C.byref(st), _ptr(frames), _ptr(out), n, w, h, od, first, mode)
-    return out, mask
+    src = aligned_empty(frames.size, frames.dtype, offset); src[:] = frames.reshape(-1)
+    out = aligned_empty(frames.size, np.uint8 if (od == 8 or depth == 8) else np.uint16, offset)
+    mask = emu.emu_add_grain_frames(C.byref(st), _ptr(src), _ptr(out), n, w, h, od, first, mode)
+    return out.reshape(frames.shape), (mask if full_mask else mask & ~WIDE)
 
 
 def run_emu_inplace(emu, o: Oracle, frames, n, w, h, first=0):
@@ -85,6 +99,25 @@ def test_fast_path_is_taken_where_expected(emu):
     assert mask_of("fgs_afgs1_test1.cfg|d10|420|g100", 200, 64) == 33  # luma rows qualify, chroma width 100 takes the fast code's EDGE variant
     assert mask_of("fgs_afgs1_test1.cfg|d10|420|g100", 204, 64) == 32  # ragged everywhere: EDGE variant for all three
     assert mask_of("fgs_sei.cfg|d10|420|g100", 204, 64) == 34          # sample-adaptive luma on ragged rows: general code
+
+
+def test_wide_path_is_taken_where_expected(emu):
+    """16 samples per lane: widths that are multiples of 16 on rows aligned to the access size (32 bytes for 10-bit
+    samples: one 256-bit access per line and lane); anything else keeps 8 samples per lane. Same output either way."""
+    for case in ("fgs_afgs1_test1.cfg|d10|420|g100", "fgs_sei_ff_test4.cfg|d10|444|g150", "fgs_sei_ff_test1.cfg|d8|420|g100"):
+        meta = G.cases[case]
+        for od in ((0, 8) if meta["depth"] == 10 else (0,)):
+            for (w, h, offset, wide) in ((512, 40, 0, True), (512, 40, 16, meta["depth"] == 8 or None), (512, 40, 8, False), (264, 40, 0, False),
+                                         (1920, 24, 0, True)):
+                if wide is None:
+                    wide = False  # 10-bit rows 16 bytes off a 32-byte boundary: 256-bit loads impossible
+                o = Oracle(); program_case(o, G, case)
+                frames = synth_frames(2, w, h, meta["fmt"], meta["depth"], seed=w + od + offset)
+                got, mask = run_emu(emu, o, frames, 2, w, h, od, offset=offset, full_mask=True)
+                want = o.add_grain_frames(frames, 2, w, h, od)
+                assert np.array_equal(got, want), (case, w, h, od, offset, first_mismatch(got, want, w, h, meta["fmt"], 2))
+                assert bool(mask & WIDE) == wide, (case, w, h, od, offset, mask)
+                assert mask & (1 | 32) and not mask & 2            # fast task code (its EDGE variant on rows off a 16-byte boundary)
 
 
 def test_fast_path_garbage_samples_and_minus_128(emu):

@@ -38,7 +38,7 @@ def test_headline_config_layout(emu):
     assert p["fimg_bytes"][0] == 2 * 2 * 64 * 72 and p["fimg_bytes"][1] == 2 * 4 * 32 * 40
     assert p["fimg_bytes"][2] == 0 and p["fimg_off"][2] == p["fimg_off"][1]  # Cr shares Cb's image
     assert all(off < 0 for off in p["fimg_off"])                           # in front of the first LUT
-    assert p["units"] == [480, 240, 240] and p["fwide"] == [0, 0, 0]
+    assert p["units"] == [240, 120, 120] and p["fwide"] == [1, 1, 1]         # 16 samples per lane, one 256-bit access per line
 
 
 def test_kernel_choice(emu):
@@ -72,3 +72,15 @@ def test_wide_path_of_8bit_input(emu):
     assert p["fwide"] == [1, 1, 1] and p["units"] == [120, 60, 60]
     p = plan(emu, o, 1936, 1080)                                            # chroma width 968 = 16 * 60.5
     assert p["fwide"] == [1, 0, 0] and p["units"] == [121, 121, 121]
+
+
+def test_wide_path_of_16bit_input(emu):
+    """10-bit samples: 16 per lane where width % 16 == 0 and rows, planes and frames are 32-byte aligned (256-bit loads;
+    the output of the fused 10 -> 8 conversion needs 16)."""
+    o = Oracle(); program_case(o, G, "fgs_afgs1_test1.cfg|d10|420|g100")
+    p = plan(emu, o, 1920, 1080)
+    assert p["fwide"] == [1, 1, 1] and p["units"] == [120, 60, 60]
+    p = plan(emu, o, 1936, 1080)                                            # chroma width 968 = 16 * 60.5: 8 samples per lane
+    assert p["fwide"] == [1, 0, 0] and p["units"] == [121, 121, 121]
+    p = plan(emu, o, 1928, 1080)                                            # luma 1928 = 16 * 120.5; chroma 964 is ragged (EDGE)
+    assert p["fwide"] == [0, 0, 0] and p["kind"] == [FAST, 3, 3]

@@ -228,6 +228,35 @@ VFGS_HD void ld_global_8_if(const uint8_t* p, uint32_t r[2], bool pred)
 #endif
 }
 
+// 256-bit accesses (sm_100: LDG.256 / STG.256), 32-byte aligned: the wide 16-bit path, one per line and lane
+VFGS_HD void ld_global_32(const uint8_t* p, uint32_t r[8])
+{
+#if defined(__CUDA_ARCH__)
+	asm volatile("ld.global" VFGS_LD_OP ".v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
+#else
+	memcpy(r, p, 32);
+#endif
+}
+VFGS_HD void ld_global_32_if(const uint8_t* p, uint32_t r[8], bool pred)
+{
+#if defined(__CUDA_ARCH__)
+	asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %9, 0;\n\t@q ld.global" VFGS_LD_OP ".v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t}"
+	             : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]) : "l"(p), "r"((uint32_t)pred));
+#else
+	if (pred) memcpy(r, p, 32);
+#endif
+}
+VFGS_HD void st_global_32(uint8_t* p, const uint32_t r[8])
+{
+#if defined(__CUDA_ARCH__)
+	asm volatile("st.global" VFGS_ST_OP ".v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+	             :: "l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+#else
+	memcpy(p, r, 32);
+#endif
+}
+
 // 8 consecutive pattern bytes at address a, a % 8 == 0: the image holds every pattern in as many
 // column-shifted copies as the window column has residues modulo 8 (fast_copies), and the block's window
 // offset (window_offset) selects the copy in which the window starts on an 8-byte boundary.
@@ -451,6 +480,38 @@ VFGS_HD void scale_add_clip_8bit(smem_addr_t lut, uint32_t lo2, uint32_t hi2, co
 	out1 = prmt(r[2], r[3], 0x6420);
 }
 
+// Scale, add, clip of 8 samples held in four words of two 10-bit samples (vfgs_hw.c:239, 260-267) and the optional
+// 10 -> 8 bit conversion (yuv.c:231). The LUT holds scale * 2^(16 - shift), so the rounded quotient of vfgs_hw.c:263 is
+// exactly the upper half-word of lut * grain + 0x8000. 8-bit output ((x + 2) >> 2): the + 2 rides on the rounding
+// constant and on the clip range (the callers pass lo + 2, hi + 2): clip(v + d, lo, hi) + 2 == clip(v + d + 2, lo + 2, hi + 2).
+// outw: 4 words (16-bit output) or 2 (8-bit).
+template <bool OUT8>
+VFGS_HD void scale_add_clip_16bit(smem_addr_t lut, uint32_t lo2, uint32_t hi2, const int g[8], const uint32_t raw[4], uint32_t* outw)
+{
+	constexpr int kRound = OUT8 ? 0x28000 : 0x8000;
+	uint32_t r[4];
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		// LUT index = (sample >> 2) & 0xff (vfgs_hw.c:211), times the 128-byte LUT row pitch
+		const int s_lo = (int)lds32(lut | (smem_addr_t)((raw[k] << 5) & 0x7f80u));
+		const int s_hi = (int)lds32(lut | (smem_addr_t)(shr_fma<11>(raw[k]) & 0x7f80u));
+		const int a_lo = s_lo * g[2 * k] + kRound;
+		const int a_hi = s_hi * g[2 * k + 1] + kRound;
+		const uint32_t d2 = prmt((uint32_t)a_lo, (uint32_t)a_hi, 0x7632);
+		// samples above 0x3fff clip to the ceiling whatever the grain: cap them so the signed 16-bit add cannot wrap
+		const uint32_t v2 = min_u16x2(raw[k], 0x3fff3fffu);
+		r[k] = min_s16x2(add_max_s16x2(v2, d2, lo2), hi2);  // vfgs_hw.c:265
+	}
+	if (OUT8) {
+#pragma unroll
+		for (int k = 0; k < 4; k++) r[k] >>= 2; // bits leaking across the half-words land in bytes 1 and 3, which are dropped
+		outw[0] = prmt(r[0], r[1], 0x6420);
+		outw[1] = prmt(r[2], r[3], 0x6420);
+	} else {
+		outw[0] = r[0]; outw[1] = r[1]; outw[2] = r[2]; outw[3] = r[3];
+	}
+}
+
 // One line of one lane. raw: the lane's 8 samples as loaded (IN16: 4 words of two 10-bit samples,
 // else 2 words of four bytes). outw: result words ready to store (16-bit out: 4 words, 8-bit: 2).
 // rc: byte offset of this line's row inside the current block's window; w_cur != 0 selects the
@@ -502,33 +563,8 @@ VFGS_HD void fast_line(const FastLane& L, int rc, int w_cur, int w_up, const Fas
 		g[7] = L.has_right ? f7 : g[7];
 	}
 
-	// scale * grain, rounded shift (vfgs_hw.c:263): the LUT holds scale * 2^(16 - shift), so the rounded
-	// quotient is exactly the upper half-word of lut * grain + 0x8000
 	if (IN16) {
-		// 8-bit output (yuv.c:231, (x + 2) >> 2): the + 2 rides on the rounding constant and on the clip
-		// range (FastLane::lo2/hi2 hold lo + 2, hi + 2), clip(v + d, lo, hi) + 2 == clip(v + d + 2, lo + 2, hi + 2)
-		constexpr int kRound = OUT8 ? 0x28000 : 0x8000;
-		uint32_t r[4];
-#pragma unroll
-		for (int k = 0; k < 4; k++) {
-			// LUT index = (sample >> 2) & 0xff (vfgs_hw.c:211), times the 128-byte LUT row pitch
-			const int s_lo = (int)lds32(L.lut | (smem_addr_t)((raw[k] << 5) & 0x7f80u));
-			const int s_hi = (int)lds32(L.lut | (smem_addr_t)(shr_fma<11>(raw[k]) & 0x7f80u));
-			const int a_lo = s_lo * g[2 * k] + kRound;
-			const int a_hi = s_hi * g[2 * k + 1] + kRound;
-			const uint32_t d2 = prmt((uint32_t)a_lo, (uint32_t)a_hi, 0x7632);
-			// samples above 0x3fff clip to the ceiling whatever the grain: cap them so the signed 16-bit add cannot wrap
-			const uint32_t v2 = min_u16x2(raw[k], 0x3fff3fffu);
-			r[k] = min_s16x2(add_max_s16x2(v2, d2, L.lo2), L.hi2);  // vfgs_hw.c:265
-		}
-		if (OUT8) {
-#pragma unroll
-			for (int k = 0; k < 4; k++) r[k] >>= 2; // bits leaking across the half-words land in bytes 1 and 3, which are dropped
-			outw[0] = prmt(r[0], r[1], 0x6420);
-			outw[1] = prmt(r[2], r[3], 0x6420);
-		} else {
-			outw[0] = r[0]; outw[1] = r[1]; outw[2] = r[2]; outw[3] = r[3];
-		}
+		scale_add_clip_16bit<OUT8>(L.lut, L.lo2, L.hi2, g, raw, outw);
 	} else {
 		scale_add_clip_8bit(L.lut, L.lo2, L.hi2, g, raw[0], raw[1], outw[0], outw[1]);
 	}
@@ -693,11 +729,13 @@ VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, const TaskGeom&
 	else lines(std::false_type());
 }
 
-// ---- 8-bit input, 16 samples per lane ------------------------------------------------------
-// With 8-bit samples a 128-bit access holds 16 samples, so a lane can own a whole 16-sample block (or two
-// 8-sample blocks): the per-line work that does not depend on the sample count (addresses, loop control,
-// halo loads, edge filters without left/right selection) and the per-task set-up are spread over twice the
-// samples. Taken when the component's width is a multiple of 16 and its rows are 16-byte aligned.
+// ---- 16 samples per lane ---------------------------------------------------------------------
+// A lane that owns a whole 16-sample block (or two 8-sample blocks) spreads the per-line work that does not depend on
+// the sample count (addresses, loop control, halo loads, edge filters without left/right selection) and the per-task
+// set-up over twice the samples. With 8-bit samples that is one 128-bit access per line; with 16-bit samples one
+// 256-bit access (LDG.256 / STG.256, sm_100), 128-bit for the 8-bit output of the fused 10 -> 8 conversion. Taken when
+// the component's width is a multiple of 16 and its rows are aligned to the access size (plan_launches, FgsParams::fwide).
+// (Round 2, measured under the sustained protocol: profiles/r02_wide16_ab.md.)
 struct WideLane {
 	smem_addr_t own0, own1;  // pattern rows of line j = 0: samples 0..7 and 8..15 (two blocks when the block size is 8)
 	smem_addr_t lh, rh;      // halo bytes: last column of the block to the left / first column of the block to the right
@@ -722,10 +760,11 @@ VFGS_HD void blend_octet(int g[8], uint32_t u0, uint32_t u1, int w_cur, int w_up
 	g[4] = blend<4>(g[4], u0, u1, w_cur, w_up); g[5] = blend<5>(g[5], u0, u1, w_cur, w_up);
 	g[6] = blend<6>(g[6], u0, u1, w_cur, w_up); g[7] = blend<7>(g[7], u0, u1, w_cur, w_up);
 }
-// One line of one wide lane: 16 samples in raw[4] (four bytes per word), result in outw[4].
-template <int NSH>
+// One line of one wide lane: 16 samples in raw (8-bit: four words of four bytes, 16-bit: eight words of two samples),
+// result in outw (four words of 8-bit samples or eight of 16-bit samples).
+template <bool IN16, bool OUT8, int NSH>
 VFGS_HD void wide_line(const WideLane& L, int rc, int w_cur, int w_up, const WideUp& U, int ru,
-                       const uint32_t raw[4], uint32_t outw[4])
+                       const uint32_t* raw, uint32_t* outw)
 {
 	uint32_t a0, a1, b0, b1;
 	octet(L.own0 + rc, a0, a1);
@@ -754,11 +793,22 @@ VFGS_HD void wide_line(const WideLane& L, int rc, int w_cur, int w_up, const Wid
 	}
 	ga[0] = L.has_left ? f0 : ga[0];
 	gb[7] = L.has_right ? f15 : gb[7];
-	scale_add_clip_8bit(L.lut, L.lo2, L.hi2, ga, raw[0], raw[1], outw[0], outw[1]);
-	scale_add_clip_8bit(L.lut, L.lo2, L.hi2, gb, raw[2], raw[3], outw[2], outw[3]);
+	if (IN16) {
+		scale_add_clip_16bit<OUT8>(L.lut, L.lo2, L.hi2, ga, raw, outw);
+		scale_add_clip_16bit<OUT8>(L.lut, L.lo2, L.hi2, gb, raw + 4, outw + (OUT8 ? 2 : 4));
+	} else {
+		scale_add_clip_8bit(L.lut, L.lo2, L.hi2, ga, raw[0], raw[1], outw[0], outw[1]);
+		scale_add_clip_8bit(L.lut, L.lo2, L.hi2, gb, raw[2], raw[3], outw[2], outw[3]);
+	}
 }
 
-template <int NSH>
+#ifndef VFGS_WIDE16_LB
+#define VFGS_WIDE16_LB 2  // lines in flight per lane of the wide 16-bit path, 16-bit output (32 bytes each)
+#endif
+#ifndef VFGS_WIDE16_LB8
+#define VFGS_WIDE16_LB8 2 // same, 8-bit output
+#endif
+template <bool IN16, bool OUT8, int NSH>
 VFGS_HD void wide_task_body(const FgsParams& p, smem_addr_t lut, const TaskGeom& t, int k0, int lane)
 {
 	const int c = t.c;
@@ -766,7 +816,10 @@ VFGS_HD void wide_task_body(const FgsParams& p, smem_addr_t lut, const TaskGeom&
 	const Plane& pl = p.comp[c];
 	const int ysh = (c && p.suby > 1) ? 1 : 0;
 	constexpr int n = 1 << NSH;
-	constexpr int LB = VFGS_FAST_LB16;
+	constexpr int LB = !IN16 ? VFGS_FAST_LB16 : OUT8 ? VFGS_WIDE16_LB8 : VFGS_WIDE16_LB;
+	static_assert(LB >= 2, "both vertical-overlap lines of a block-row must fall into the first group of lines");
+	constexpr int IB = IN16 ? 2 : 1, OB = (IN16 && !OUT8) ? 2 : 1;
+	constexpr int RW = IN16 ? 8 : 4, OW = OB == 2 ? 8 : 4; // words per line: loaded, stored
 
 	const int cl0 = (t.r * 16) >> ysh;
 	int cl1 = cl0 + (16 >> ysh);
@@ -775,12 +828,15 @@ VFGS_HD void wide_task_body(const FgsParams& p, smem_addr_t lut, const TaskGeom&
 	if (nl <= 0) return;
 
 	const long long in_pitch = pl.in_row_bytes, out_pitch = pl.out_row_bytes;
-	const uint8_t* src = pl.in + (long long)t.f * p.in_frame_bytes + (long long)cl0 * in_pitch + (long long)k0;
-	uint8_t* dst = pl.out + (long long)t.f * p.out_frame_bytes + (long long)cl0 * out_pitch + (long long)k0;
+	const uint8_t* src = pl.in + (long long)t.f * p.in_frame_bytes + (long long)cl0 * in_pitch + (long long)k0 * IB;
+	uint8_t* dst = pl.out + (long long)t.f * p.out_frame_bytes + (long long)cl0 * out_pitch + (long long)k0 * OB;
 
-	uint32_t raw[LB][4];
+	uint32_t raw[LB][RW];
 #pragma unroll
-	for (int q = 0; q < LB; q++) ld_global_16(src + (q < nl ? q : nl - 1) * in_pitch, raw[q]);
+	for (int q = 0; q < LB; q++) {
+		if (IN16) ld_global_32(src + (q < nl ? q : nl - 1) * in_pitch, raw[q]);
+		else ld_global_16(src + (q < nl ? q : nl - 1) * in_pitch, raw[q]);
+	}
 
 	// first and last block of the lane (the same one with 16-sample blocks)
 	const int b0 = k0 >> NSH, b1 = (k0 + 15) >> NSH;
@@ -789,7 +845,8 @@ VFGS_HD void wide_task_body(const FgsParams& p, smem_addr_t lut, const TaskGeom&
 	L.has_right = b1 + 1 < p.nb;
 	L.stride = p.fpat_stride[c];
 	L.lut = lut + (smem_addr_t)(c * kLutBytes + lane * 4);
-	L.lo2 = (uint32_t)p.lo[c] * 0x00010001u; L.hi2 = (uint32_t)p.hi[c] * 0x00010001u;
+	constexpr int kOutBias = (IN16 && OUT8) ? 2 : 0; // see scale_add_clip_16bit
+	L.lo2 = (uint32_t)(p.lo[c] + kOutBias) * 0x00010001u; L.hi2 = (uint32_t)(p.hi[c] + kOutBias) * 0x00010001u;
 
 	const int srow = t.r - p.stream_row0;
 	const uint16_t* w_cur = p.woffs + (((long long)t.f * p.stream_rows + srow) * p.spitch + 1 + b0) * 4 + c;
@@ -813,13 +870,17 @@ VFGS_HD void wide_task_body(const FgsParams& p, smem_addr_t lut, const TaskGeom&
 #pragma unroll
 		for (int q = 0; q < LB; q++) {
 			const int line = base + q;
-			uint32_t w[4];
+			uint32_t w[OW];
 			int wc = 0, wu = 0, ru = 0;
 			if (q == 0 && ovl) { wc = ysh ? 20 : 12; wu = ysh ? 20 : 24; ru = (16 >> ysh) * L.stride; }
 			if (q == 1 && ovl && !ysh) { wc = 24; wu = 12; ru = 17 * L.stride; }
-			wide_line<NSH>(L, rc, wc, wu, U, ru, raw[q], w);
-			ld_global_16_if(nxt, raw[q], line + LB < nl);
-			if (line < nl) st_global_16(dst, w);
+			wide_line<IN16, OUT8, NSH>(L, rc, wc, wu, U, ru, raw[q], w);
+			if (IN16) ld_global_32_if(nxt, raw[q], line + LB < nl);
+			else ld_global_16_if(nxt, raw[q], line + LB < nl);
+			if (line < nl) {
+				if (OB == 2) st_global_32(dst, w);
+				else st_global_16(dst, w);
+			}
 			rc += L.stride; nxt += in_pitch; dst += out_pitch;
 		}
 		ovl = false;
@@ -829,7 +890,7 @@ VFGS_HD void wide_task_body(const FgsParams& p, smem_addr_t lut, const TaskGeom&
 // Dispatch on the component's block size (16 samples: luma and non-subsampled chroma; 8: chroma
 // subsampled horizontally).
 // Fast-kernel task numbering: per frame the components one after the other; inside a component the
-// stripes' rows are one flat run of lane units (8 samples, or 16 on the wide 8-bit path: FgsParams::fwide), 32
+// stripes' rows are one flat run of lane units (8 samples, or 16 on the wide path: FgsParams::fwide), 32
 // consecutive units per warp-task, so only the very last task of a component can have idle lanes (a row need
 // not be a multiple of 256 samples).
 template <bool IN16, bool OUT8, bool EDGE = false>
@@ -847,10 +908,10 @@ VFGS_HD void process_task_fast(const FgsParams& p, smem_addr_t lut, uint32_t tas
 	const uint32_t row = fastdiv(unit, p.div_funits[t.c]);
 	t.r = p.row_begin + (int)row;
 	t.seg = 0;
-	if (!IN16 && !EDGE && p.fwide[t.c]) { // 8-bit samples, 16 per lane
+	if (!EDGE && p.fwide[t.c]) { // 16 samples per lane
 		const int k0 = (int)(unit - row * upr) * 16;
-		if (t.c && p.subx > 1) wide_task_body<3>(p, lut, t, k0, lane);
-		else wide_task_body<4>(p, lut, t, k0, lane);
+		if (t.c && p.subx > 1) wide_task_body<IN16, OUT8, 3>(p, lut, t, k0, lane);
+		else wide_task_body<IN16, OUT8, 4>(p, lut, t, k0, lane);
 		return;
 	}
 	const int k0 = (int)(unit - row * upr) * kSamplesPerLane;

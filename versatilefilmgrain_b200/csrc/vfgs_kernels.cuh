@@ -142,7 +142,7 @@ fgs_apply_kernel(const __grid_constant__ FgsParams p)
 // outstanding lines per SM lower the DRAM efficiency again: 768 threads 95.6 %, 1024 threads 89 % of the
 // measured copy bandwidth at 4K).
 #ifndef VFGS_FAST_THREADS8
-#define VFGS_FAST_THREADS8 1024  // 16-bit in, 8-bit out
+#define VFGS_FAST_THREADS8 768   // 16-bit in, 8-bit out
 #endif
 #ifndef VFGS_FAST_THREADS16
 #define VFGS_FAST_THREADS16 768  // 16-bit in, 16-bit out

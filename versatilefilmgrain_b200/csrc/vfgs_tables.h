@@ -14,6 +14,9 @@
 #ifndef VFGS_FAST_WIDE8
 #define VFGS_FAST_WIDE8 1 // 8-bit input: 16 samples per lane where possible (build-time knob for experiments)
 #endif
+#ifndef VFGS_FAST_WIDE16
+#define VFGS_FAST_WIDE16 1 // 16-bit input: the same with 256-bit accesses (build-time knob for experiments)
+#endif
 #ifndef VFGS_FAST_ROW_SKEW
 #define VFGS_FAST_ROW_SKEW 8 // bytes, multiple of 8 (build-time knob for experiments)
 #endif
@@ -314,10 +317,11 @@ inline void plan_launches(const FgsParams& p, const TableInfo& bi, int mode, boo
 		FgsParams& f = which ? lp.edge : lp.fast;
 		f.ftasks_per_frame = 0;
 		for (int c = 0; c < 3; c++) {
-			// 8-bit samples: 16 per lane where the rows allow 128-bit accesses
-			f.fwide[c] = VFGS_FAST_WIDE8 && kind[c] == 0 && k == 0 && f.in_bytes == 1 && f.comp[c].width % 16 == 0 &&
-			             aligned_for(f.comp[c].in, f.comp[c].in_row_bytes, f.in_frame_bytes, 16) &&
-			             aligned_for(f.comp[c].out, f.comp[c].out_row_bytes, f.out_frame_bytes, 16);
+			// 16 samples per lane where the rows allow one access per line and lane (128-bit for 8-bit samples, 256-bit for 16-bit ones)
+			const bool wide_on = f.in_bytes == 1 ? VFGS_FAST_WIDE8 != 0 : VFGS_FAST_WIDE16 != 0;
+			f.fwide[c] = wide_on && kind[c] == 0 && k == 0 && f.comp[c].width % 16 == 0 &&
+			             aligned_for(f.comp[c].in, f.comp[c].in_row_bytes, f.in_frame_bytes, (size_t)(16 * f.in_bytes)) &&
+			             aligned_for(f.comp[c].out, f.comp[c].out_row_bytes, f.out_frame_bytes, (size_t)(16 * f.out_bytes));
 			f.funits_per_row[c] = kind[c] == k ? (f.comp[c].width + (f.fwide[c] ? 16 : kSamplesPerLane) - 1) / (f.fwide[c] ? 16 : kSamplesPerLane) : 0;
 			f.ftasks[c] = (f.funits_per_row[c] * f.rows + 31) / 32;
 			f.ftasks_per_frame += f.ftasks[c];

@@ -17,7 +17,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 from oracle.pyoracle import RefState, _ptr  # noqa: E402
-from tests.util import Oracle, build_emu, first_mismatch, program_random_state, synth_frames  # noqa: E402
+from tests.util import Oracle, aligned_empty, build_emu, first_mismatch, program_random_state, synth_frames  # noqa: E402
 
 WIDTHS = [136, 144, 152, 160, 200, 203, 256, 264, 270, 272, 366, 512, 520, 523, 528, 1040]
 
@@ -36,13 +36,17 @@ def one_case(emu, rng):
         o = Oracle(); program_random_state(o, *spec)
         st = RefState(); o.L.oracle_get_state(o.h, C.byref(st))
         first = int(rng.integers(0, 5000)) if rng.integers(0, 3) == 0 else 0  # frames of a sequence already under way
+        # buffer alignment decides between 16 samples per lane (32-byte aligned rows), 8 samples per lane and the EDGE variant
+        offset = int(rng.choice([0, 0, 0, 32, 16, 8, 4, 2])) & ~(frames.itemsize - 1)
+        src = aligned_empty(frames.size, frames.dtype, offset); src[:] = frames.reshape(-1)
+        frames = src
         outs = []
         for mode in (0, 1, 2):
-            out = np.zeros(frames.shape, dtype=np.uint8 if (od == 8 or depth == 8) else np.uint16)
+            out = aligned_empty(frames.size, np.uint8 if (od == 8 or depth == 8) else np.uint16, int(rng.choice([offset, 0])))
             emu.emu_add_grain_frames(C.byref(st), _ptr(frames), _ptr(out), n, w, h, od, first, mode)
-            outs.append((f"mode={mode}", out))
+            outs.append((f"mode={mode} offset={offset}", out))
         if od == 0:  # same depth in and out: in place as well
-            buf = frames.copy()
+            buf = aligned_empty(frames.size, frames.dtype, offset); buf[:] = frames
             mask = emu.emu_add_grain_frames(C.byref(st), _ptr(buf), _ptr(buf), n, w, h, od, first, 0)
             # sample-adaptive components on the general task code read neighbouring input samples: the shim sends those
             # calls through a scratch buffer (vfgs_b200.cu, in_place_needs_scratch), the emulation has none

@@ -23,11 +23,11 @@ struct StateDump { // == refh_state / oracle_dump
 	int scale_shift, bs, y_min, y_max, c_min, c_max, csubx, csuby;
 };
 
-template <bool IN16, bool OUT8, bool EDGE>
+template <bool IN16, bool OUT8, bool EDGE, bool ALLWIDE = false>
 void run_fast(const FgsParams& p, const uint8_t* lut)
 {
 	for (long long task = 0; task < p.total_tasks; task++)
-		for (int lane = 0; lane < 32; lane++) process_task_fast<IN16, OUT8, EDGE>(p, smem_addr(lut), (uint32_t)task, lane);
+		for (int lane = 0; lane < 32; lane++) process_task_fast<IN16, OUT8, EDGE, ALLWIDE>(p, smem_addr(lut), (uint32_t)task, lane);
 }
 
 // the gather task code exchanges grain values between lanes (warp shuffle on the device): every task runs twice,
@@ -144,6 +144,7 @@ extern "C" int emu_add_grain_frames(const void* state, const void* in, void* out
 		expand_fast_luts((uint32_t*)lut_ptr, (const uint32_t*)fblob.data(), (uint32_t)(1 << (16 - h.scale_shift)), 0, 1);
 		if (isz == 1) run_fast<false, false, false>(f, lut_ptr);
 		else if (osz == 1) run_fast<true, true, false>(f, lut_ptr);
+		else if (f.fallwide) run_fast<true, false, false, true>(f, lut_ptr); // the ALLWIDE kernel variant, like launch_apply
 		else run_fast<true, false, false>(f, lut_ptr);
 	}
 	if (lp.any_edge) { // the EDGE launch of the fast kernel: same shared-memory image, its own components

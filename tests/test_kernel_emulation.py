@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle.pyoracle import RefState, _ptr
-from tests.util import Oracle, build_emu, first_mismatch, load_golden, program_case, synth_frames
+from tests.util import Oracle, aligned_empty, build_emu, first_mismatch, load_golden, program_case, synth_frames
 
 G = load_golden()
 CASES = G.runnable()
@@ -22,14 +22,6 @@ def emu():
 
 
 WIDE = 64  # mask bit: some component of the fast launch ran 16 samples per lane
-
-
-def aligned_empty(n, dtype, offset=0):
-    """n elements whose first byte sits `offset` bytes after a 64-byte boundary (numpy itself only promises 16)."""
-    item = np.dtype(dtype).itemsize
-    raw = np.zeros(n * item + 128, dtype=np.uint8)
-    start = (-raw.ctypes.data) % 64 + offset
-    return raw[start:start + n * item].view(dtype)
 
 
 def run_emu(emu, o: Oracle, frames, n, w, h, od, first=0, mode=0, offset=0, full_mask=False):

@@ -99,3 +99,12 @@ RANDOM_STATES = [
     # found by fuzzing the emulated kernels: Cb sample-adaptive (gather kernel), Cr one slot (fast kernel, own image)
     (6605739, 10, "422", 4, 2, 0, 7, False), (765400224, 10, "444", 6, 2, 1, 5, False),
 ]
+
+
+def aligned_empty(n, dtype, offset=0):
+    """n zeroed elements whose first byte sits `offset` bytes after a 64-byte boundary (numpy itself only promises 16):
+    the 16-samples-per-lane paths of the fast kernel need 16 / 32-byte aligned rows."""
+    item = np.dtype(dtype).itemsize
+    raw = np.zeros(n * item + 128, dtype=np.uint8)
+    start = (-raw.ctypes.data) % 64 + offset
+    return raw[start:start + n * item].view(dtype)

@@ -619,6 +619,9 @@ static_assert(kFastLB >= 2, "both vertical-overlap lines of a block-row must fal
 #ifndef VFGS_FAST_LB8
 #define VFGS_FAST_LB8 VFGS_FAST_LB  // fast kernel, 16-bit in, 8-bit out
 #endif
+#ifndef VFGS_NARROW16_LB
+#define VFGS_NARROW16_LB VFGS_FAST_LB16 // 16-bit in and out, 8 samples per lane (widths that are not a multiple of 16 samples)
+#endif
 
 // EDGE: rows at any sample-aligned address, partial last unit of a row (see edge_load / edge_store above)
 template <bool IN16, bool OUT8, int NSH, bool EDGE = false>
@@ -629,7 +632,7 @@ VFGS_HD void fast_task_body(const FgsParams& p, smem_addr_t lut, const TaskGeom&
 	const Plane& pl = p.comp[c];
 	const int ysh = (c && p.suby > 1) ? 1 : 0;
 	constexpr int n = 1 << NSH;
-	constexpr int LB = OUT8 ? VFGS_FAST_LB8 : VFGS_FAST_LB16; // lines in flight per lane
+	constexpr int LB = OUT8 ? VFGS_FAST_LB8 : IN16 ? VFGS_NARROW16_LB : VFGS_FAST_LB16; // lines in flight per lane
 
 	// component lines of this stripe (whole stripes only: the host sends partial line ranges to
 	// the general kernel)
@@ -802,13 +805,18 @@ VFGS_HD void wide_line(const WideLane& L, int rc, int w_cur, int w_up, const Wid
 	}
 }
 
+// Lines in flight per lane of the wide 16-bit path (32 bytes each), measured with the CTA sizes of vfgs_kernels.cuh
+// (profiles/r02_wide16_ab.md): odd counts lose 4-10 points (a stripe's 16 lines are then not a whole number of groups).
 #ifndef VFGS_WIDE16_LB
-#define VFGS_WIDE16_LB 2  // lines in flight per lane of the wide 16-bit path, 16-bit output (32 bytes each)
+#define VFGS_WIDE16_LB 2   // 16-bit output, kernel shared with 8-samples-per-lane components (768 threads)
+#endif
+#ifndef VFGS_WIDE16_LBW
+#define VFGS_WIDE16_LBW 4  // 16-bit output, every component wide (ALLWIDE variant: 512 threads, 128 registers)
 #endif
 #ifndef VFGS_WIDE16_LB8
-#define VFGS_WIDE16_LB8 2 // same, 8-bit output
+#define VFGS_WIDE16_LB8 2  // 8-bit output (768 threads)
 #endif
-template <bool IN16, bool OUT8, int NSH>
+template <bool IN16, bool OUT8, int NSH, bool ALLWIDE = false>
 VFGS_HD void wide_task_body(const FgsParams& p, smem_addr_t lut, const TaskGeom& t, int k0, int lane)
 {
 	const int c = t.c;
@@ -816,7 +824,7 @@ VFGS_HD void wide_task_body(const FgsParams& p, smem_addr_t lut, const TaskGeom&
 	const Plane& pl = p.comp[c];
 	const int ysh = (c && p.suby > 1) ? 1 : 0;
 	constexpr int n = 1 << NSH;
-	constexpr int LB = !IN16 ? VFGS_FAST_LB16 : OUT8 ? VFGS_WIDE16_LB8 : VFGS_WIDE16_LB;
+	constexpr int LB = !IN16 ? VFGS_FAST_LB16 : OUT8 ? VFGS_WIDE16_LB8 : ALLWIDE ? VFGS_WIDE16_LBW : VFGS_WIDE16_LB;
 	static_assert(LB >= 2, "both vertical-overlap lines of a block-row must fall into the first group of lines");
 	constexpr int IB = IN16 ? 2 : 1, OB = (IN16 && !OUT8) ? 2 : 1;
 	constexpr int RW = IN16 ? 8 : 4, OW = OB == 2 ? 8 : 4; // words per line: loaded, stored
@@ -893,7 +901,9 @@ VFGS_HD void wide_task_body(const FgsParams& p, smem_addr_t lut, const TaskGeom&
 // stripes' rows are one flat run of lane units (8 samples, or 16 on the wide path: FgsParams::fwide), 32
 // consecutive units per warp-task, so only the very last task of a component can have idle lanes (a row need
 // not be a multiple of 256 samples).
-template <bool IN16, bool OUT8, bool EDGE = false>
+// ALLWIDE: every component of the launch takes the 16-samples-per-lane path (FgsParams::fallwide); the kernel variant then
+// has its own CTA size and more lines in flight per lane.
+template <bool IN16, bool OUT8, bool EDGE = false, bool ALLWIDE = false>
 VFGS_HD void process_task_fast(const FgsParams& p, smem_addr_t lut, uint32_t task, int lane)
 {
 	TaskGeom t;
@@ -908,12 +918,14 @@ VFGS_HD void process_task_fast(const FgsParams& p, smem_addr_t lut, uint32_t tas
 	const uint32_t row = fastdiv(unit, p.div_funits[t.c]);
 	t.r = p.row_begin + (int)row;
 	t.seg = 0;
-	if (!EDGE && p.fwide[t.c]) { // 16 samples per lane
+	static_assert(!(ALLWIDE && EDGE), "the EDGE variant has no wide path");
+	if (ALLWIDE || (!EDGE && p.fwide[t.c])) { // 16 samples per lane
 		const int k0 = (int)(unit - row * upr) * 16;
-		if (t.c && p.subx > 1) wide_task_body<IN16, OUT8, 3>(p, lut, t, k0, lane);
-		else wide_task_body<IN16, OUT8, 4>(p, lut, t, k0, lane);
+		if (t.c && p.subx > 1) wide_task_body<IN16, OUT8, 3, ALLWIDE>(p, lut, t, k0, lane);
+		else wide_task_body<IN16, OUT8, 4, ALLWIDE>(p, lut, t, k0, lane);
 		return;
 	}
+	if (ALLWIDE) return;
 	const int k0 = (int)(unit - row * upr) * kSamplesPerLane;
 	if (t.c && p.subx > 1) fast_task_body<IN16, OUT8, 3, EDGE>(p, lut, t, k0, lane);
 	else fast_task_body<IN16, OUT8, 4, EDGE>(p, lut, t, k0, lane);

@@ -170,10 +170,12 @@ int ensure_ctx(int device)
 		fgs_apply_fast_kernel<true, true><<<1, 32, 1024>>>(pp);
 		pp.probe = d_probe + 2;
 		fgs_apply_fast_kernel<false, false><<<1, 32, 1024>>>(pp);
-		uint32_t pads[3] = {0, 0, 0};
+		pp.probe = d_probe + 3;
+		fgs_apply_fast_kernel<true, false, false, true><<<1, 32, 1024>>>(pp);
+		uint32_t pads[4] = {0, 0, 0, 0};
 		CUDA_TRY(cudaMemcpy(pads, d_probe, sizeof(pads), cudaMemcpyDeviceToHost));
-		if (pads[0] != pads[1] || pads[0] != pads[2])
-			return set_err(VFGS_B200_ERR_CUDA, "fast kernel variants place dynamic shared memory differently (%u, %u, %u)", pads[0], pads[1], pads[2]);
+		if (pads[0] != pads[1] || pads[0] != pads[2] || pads[0] != pads[3])
+			return set_err(VFGS_B200_ERR_CUDA, "fast kernel variants place dynamic shared memory differently (%u, %u, %u, %u)", pads[0], pads[1], pads[2], pads[3]);
 		c.fast_pad = (int)pads[0];
 	}
 	CUDA_TRY(cudaMemcpy(c.d_pow2, jump_table().pow2, sizeof(uint32_t) * kJumpBits * 32, cudaMemcpyHostToDevice));
@@ -333,13 +335,16 @@ int launch_apply(const FgsParams& p, cudaStream_t stream, KernelKind kind = kGen
 	GrainKernel kern = fgs_apply_kernel;
 	int threads = kCtaThreads, smem = p.blob_bytes;
 	if (kind == kFast || kind == kFastEdge) {
-		if (kind == kFast)
+		const bool allwide = kind == kFast && p.in_bytes == 2 && p.out_bytes == 2 && p.fallwide;
+		if (allwide)
+			kern = fgs_apply_fast_kernel<true, false, false, true>;
+		else if (kind == kFast)
 			kern = p.in_bytes == 1 ? fgs_apply_fast_kernel<false, false>
 			     : p.out_bytes == 1 ? fgs_apply_fast_kernel<true, true> : fgs_apply_fast_kernel<true, false>;
 		else
 			kern = p.in_bytes == 1 ? fgs_apply_fast_kernel<false, false, true>
 			     : p.out_bytes == 1 ? fgs_apply_fast_kernel<true, true, true> : fgs_apply_fast_kernel<true, false, true>;
-		threads = fast_threads(p.in_bytes == 2, p.in_bytes == 2 && p.out_bytes == 1, kind == kFastEdge); smem = p.fsmem;
+		threads = fast_threads(p.in_bytes == 2, p.in_bytes == 2 && p.out_bytes == 1, kind == kFastEdge, allwide); smem = p.fsmem;
 		if (smem > c.fast_smem_attr) {
 			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_fast_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_fast_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -347,6 +352,7 @@ int launch_apply(const FgsParams& p, cudaStream_t stream, KernelKind kind = kGen
 			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_fast_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_fast_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_fast_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+			CUDA_TRY(cudaFuncSetAttribute(fgs_apply_fast_kernel<true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 			c.fast_smem_attr = smem;
 		}
 	} else if (kind == kGather) {

@@ -170,7 +170,8 @@ struct FgsParams {
 	// fast kernel task numbering: a component's stripes are one flat run of 8-sample lane units
 	// (units_per_row * rows of them per frame), cut into warp-tasks of 32 units regardless of row ends
 	int funits_per_row[3], ftasks[3], ftasks_per_frame;
-	int fwide[3];           // 8-bit input: the component's lane units are 16 samples (fgs_fast.h, wide_task_body)
+	int fwide[3];           // the component's lane units are 16 samples (fgs_fast.h, wide_task_body)
+	int fallwide;           // every component this launch serves is wide (selects the ALLWIDE kernel variant)
 	FastDiv div_funits[3], div_ftasks;
 	// table image ("blob") copied to shared memory by every CTA
 	const uint8_t* blob;

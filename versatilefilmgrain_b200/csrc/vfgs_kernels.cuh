@@ -153,19 +153,24 @@ fgs_apply_kernel(const __grid_constant__ FgsParams p)
 #ifndef VFGS_FAST_THREADS_EDGE
 #define VFGS_FAST_THREADS_EDGE 768  // EDGE variants (ragged / unaligned rows): the piecewise accesses want the 85 registers of 24 warps
 #endif
-template <bool IN16, bool OUT8, bool EDGE = false> struct FastCta {
-	static constexpr int threads = EDGE ? VFGS_FAST_THREADS_EDGE : !IN16 ? VFGS_FAST_THREADS_IN8 : OUT8 ? VFGS_FAST_THREADS8 : VFGS_FAST_THREADS16;
+#ifndef VFGS_FAST_THREADS16W
+#define VFGS_FAST_THREADS16W 512 // 16-bit in, 16-bit out, every component on the 16-samples-per-lane path (ALLWIDE): 128 registers hold four
+                                 // 32-byte lines per lane; 4K 10-bit 0.93 (8 samples per lane) -> 0.965 (768 threads x 2 lines) -> 0.98
+#endif
+template <bool IN16, bool OUT8, bool EDGE = false, bool ALLWIDE = false> struct FastCta {
+	static_assert(!ALLWIDE || (IN16 && !OUT8 && !EDGE), "ALLWIDE exists for 16-bit input and output only");
+	static constexpr int threads = ALLWIDE ? VFGS_FAST_THREADS16W : EDGE ? VFGS_FAST_THREADS_EDGE : !IN16 ? VFGS_FAST_THREADS_IN8 : OUT8 ? VFGS_FAST_THREADS8 : VFGS_FAST_THREADS16;
 };
-inline int fast_threads(bool in16, bool out8, bool edge = false)
+inline int fast_threads(bool in16, bool out8, bool edge = false, bool allwide = false)
 {
-	return edge ? VFGS_FAST_THREADS_EDGE : !in16 ? VFGS_FAST_THREADS_IN8 : out8 ? VFGS_FAST_THREADS8 : VFGS_FAST_THREADS16;
+	return allwide ? VFGS_FAST_THREADS16W : edge ? VFGS_FAST_THREADS_EDGE : !in16 ? VFGS_FAST_THREADS_IN8 : out8 ? VFGS_FAST_THREADS8 : VFGS_FAST_THREADS16;
 }
 
-template <bool IN16, bool OUT8, bool EDGE = false>
-__global__ void __launch_bounds__(FastCta<IN16, OUT8, EDGE>::threads, 1)
+template <bool IN16, bool OUT8, bool EDGE = false, bool ALLWIDE = false>
+__global__ void __launch_bounds__(FastCta<IN16, OUT8, EDGE, ALLWIDE>::threads, 1)
 fgs_apply_fast_kernel(const __grid_constant__ FgsParams p)
 {
-	constexpr int kFastThreads = FastCta<IN16, OUT8, EDGE>::threads, kFastWarps = kFastThreads / 32;
+	constexpr int kFastThreads = FastCta<IN16, OUT8, EDGE, ALLWIDE>::threads, kFastWarps = kFastThreads / 32;
 	extern __shared__ __align__(128) uint8_t smem[];
 	__shared__ __align__(8) uint64_t bar;
 
@@ -195,7 +200,7 @@ fgs_apply_fast_kernel(const __grid_constant__ FgsParams p)
 	const smem_addr_t lut = smem_addr(lut_ptr);
 	const long long stride = (long long)gridDim.x * kFastWarps;
 	for (long long task = (long long)blockIdx.x * kFastWarps + (threadIdx.x >> 5); task < p.total_tasks; task += stride)
-		process_task_fast<IN16, OUT8, EDGE>(p, lut, (uint32_t)task, lane);
+		process_task_fast<IN16, OUT8, EDGE, ALLWIDE>(p, lut, (uint32_t)task, lane);
 }
 
 // Gather path: components with sample-adaptive pattern selection (fgs_gather.h). Shared memory: one

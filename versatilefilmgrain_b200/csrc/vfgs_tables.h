@@ -328,6 +328,9 @@ inline void plan_launches(const FgsParams& p, const TableInfo& bi, int mode, boo
 			f.div_funits[c] = make_fastdiv((uint32_t)(f.funits_per_row[c] > 0 ? f.funits_per_row[c] : 1));
 		}
 		f.div_ftasks = make_fastdiv((uint32_t)(f.ftasks_per_frame > 0 ? f.ftasks_per_frame : 1));
+		int served = 0, wide = 0;
+		for (int c = 0; c < 3; c++) if (kind[c] == k) { served++; wide += f.fwide[c] ? 1 : 0; }
+		f.fallwide = served > 0 && wide == served;
 	}
 	lp.gather_shift = in_place && ngather > 0;
 	lp.gather.ngather = ngather;

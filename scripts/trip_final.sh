@@ -22,9 +22,10 @@ rm -f gpurun_out/cli_bench.jsonl
 for od in 0 8; do timeout 300 python scripts/cli_bench.py --frames 96 --outdepth $od 2>&1 | tail -1 >> gpurun_out/cli_bench.jsonl; done; cut -c1-700 gpurun_out/cli_bench.jsonl
 BASE="python bench.py --steps 2 --warmup 3 --passes 1 --e2e-frames 4 --no-cpu-baseline --no-sustained-copy --skip-parity-gate"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv $BASE --frames-per-step 64 > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
-cap() { # name kernel-regex extra bench args...
+cap() { # name kernel-regex extra bench args...   (vfgs_b200_init launches each of the four fast-kernel variants once as a one-warp probe: skip those)
   n=$1; k=$2; shift 2
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -f -o gpurun_out/r02_$n $BASE "$@" > gpurun_out/ncu_$n.log 2>&1; echo "ncu $n rc=$?"
+  skip=3; [ "$k" = fgs_apply_fast ] && skip=7
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s $skip -c 1 -f -o gpurun_out/r02_$n $BASE "$@" > gpurun_out/ncu_$n.log 2>&1; echo "ncu $n rc=$?"
 }
 cap fast_10to10 fgs_apply_fast --frames-per-step 64 --workload 4k420_afgs1_10to10
 cap fast_10to8 fgs_apply_fast --frames-per-step 64 --workload 4k420_afgs1_10to8

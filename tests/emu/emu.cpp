@@ -184,7 +184,7 @@ extern "C" int emu_add_grain_frames(const void* state, const void* in, void* out
 
 // Launch planning of a whole-frame call, without running anything (host logic only): which kernel serves each
 // component, the fast kernel's shared-memory layout and lane-unit width. out (ints): kind[3], fsmem, fpad,
-// fimg_off[3], fimg_bytes[3], fwide[3], funits_per_row[3], gather_smem.
+// fimg_off[3], fimg_bytes[3], fwide[3], funits_per_row[3], gather_smem, fallwide.
 extern "C" void emu_plan(const void* state, int width, int height, int out_depth, int in_place, int mode, int* out)
 {
 	const StateDump& d = *(const StateDump*)state;
@@ -234,6 +234,7 @@ extern "C" void emu_plan(const void* state, int width, int height, int out_depth
 	for (int c = 0; c < 3; c++) out[k++] = lp.fast.fwide[c];
 	for (int c = 0; c < 3; c++) out[k++] = lp.fast.funits_per_row[c];
 	out[k++] = lp.gather_smem;
+	out[k++] = lp.fast.fallwide;
 }
 
 // ---- firmware layer (fw_host.h + fw_device.h run with one host thread) ---------------------------

@@ -25,7 +25,8 @@ def plan(emu, o, w, h, od=0, in_place=0, mode=0):
     out = np.zeros(20, dtype=np.int32)
     emu.emu_plan(C.byref(st), w, h, od, in_place, mode, out.ctypes.data_as(C.c_void_p))
     return {"kind": list(out[0:3]), "fsmem": int(out[3]), "fpad": int(out[4]), "fimg_off": list(out[5:8]),
-            "fimg_bytes": list(out[8:11]), "fwide": list(out[11:14]), "units": list(out[14:17]), "gather_smem": int(out[17])}
+            "fimg_bytes": list(out[8:11]), "fwide": list(out[11:14]), "units": list(out[14:17]), "gather_smem": int(out[17]),
+            "allwide": int(out[18])}
 
 
 def test_headline_config_layout(emu):
@@ -79,8 +80,11 @@ def test_wide_path_of_16bit_input(emu):
     the output of the fused 10 -> 8 conversion needs 16)."""
     o = Oracle(); program_case(o, G, "fgs_afgs1_test1.cfg|d10|420|g100")
     p = plan(emu, o, 1920, 1080)
-    assert p["fwide"] == [1, 1, 1] and p["units"] == [120, 60, 60]
+    assert p["fwide"] == [1, 1, 1] and p["units"] == [120, 60, 60] and p["allwide"] == 1   # the 512-thread ALLWIDE kernel variant
     p = plan(emu, o, 1936, 1080)                                            # chroma width 968 = 16 * 60.5: 8 samples per lane
-    assert p["fwide"] == [1, 0, 0] and p["units"] == [121, 121, 121]
+    assert p["fwide"] == [1, 0, 0] and p["units"] == [121, 121, 121] and p["allwide"] == 0  # mixed launch: the 768-thread kernel
     p = plan(emu, o, 1928, 1080)                                            # luma 1928 = 16 * 120.5; chroma 964 is ragged (EDGE)
-    assert p["fwide"] == [0, 0, 0] and p["kind"] == [FAST, 3, 3]
+    assert p["fwide"] == [0, 0, 0] and p["kind"] == [FAST, 3, 3] and p["allwide"] == 0
+    o = Oracle(); program_case(o, G, "fgs_sei.cfg|d10|420|g100")            # luma on the gather kernel: the fast launch serves chroma only
+    p = plan(emu, o, 1920, 1080)
+    assert p["kind"] == [GATHER, FAST, FAST] and p["fwide"] == [0, 1, 1] and p["allwide"] == 1

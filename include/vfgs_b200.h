@@ -61,7 +61,11 @@ size_t vfgs_b200_frame_bytes(int width, int height, int depth);
 int vfgs_b200_add_grain_frames_device(const void* in, void* out, int nframes, int width, int height,
                                       int out_depth, void* stream);
 
-/* Same with explicit planes/strides (device memory). */
+/* Same with explicit planes/strides (device memory). Any sample-aligned pointers and strides are accepted and give the
+ * same output; the speed depends on them: planes, line strides and the frame stride that are multiples of 32 bytes
+ * (16 for 8-bit samples), with widths that are multiples of 16 samples, take the 16-samples-per-lane kernels
+ * (packed frames of the usual picture sizes in cudaMalloc'd memory qualify); multiples of 16 bytes / 8 samples the
+ * 8-samples-per-lane form; anything else the EDGE variant. */
 int vfgs_b200_add_grain_planes_device(const vfgs_b200_planes* in, const vfgs_b200_planes* out,
                                       int nframes, int width, int height, int out_depth, void* stream);
 

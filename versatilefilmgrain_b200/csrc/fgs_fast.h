@@ -485,6 +485,9 @@ VFGS_HD void scale_add_clip_8bit(smem_addr_t lut, uint32_t lo2, uint32_t hi2, co
 // exactly the upper half-word of lut * grain + 0x8000. 8-bit output ((x + 2) >> 2): the + 2 rides on the rounding
 // constant and on the clip range (the callers pass lo + 2, hi + 2): clip(v + d, lo, hi) + 2 == clip(v + d + 2, lo + 2, hi + 2).
 // outw: 4 words (16-bit output) or 2 (8-bit).
+#ifndef VFGS_OUT8_MUL64
+#define VFGS_OUT8_MUL64 0 // build-time knob for experiments
+#endif
 template <bool OUT8>
 VFGS_HD void scale_add_clip_16bit(smem_addr_t lut, uint32_t lo2, uint32_t hi2, const int g[8], const uint32_t raw[4], uint32_t* outw)
 {
@@ -503,10 +506,19 @@ VFGS_HD void scale_add_clip_16bit(smem_addr_t lut, uint32_t lo2, uint32_t hi2, c
 		r[k] = min_s16x2(add_max_s16x2(v2, d2, lo2), hi2);  // vfgs_hw.c:265
 	}
 	if (OUT8) {
+		if (VFGS_OUT8_MUL64) {
+			// (x >> 2) & 0xff is byte 1 of x * 64 (FMA pipe instead of ALU); x <= 1025, so a half-word can overflow by one bit
+			// into bit 0 of its neighbour, whose low six bits are zero (no carry) and lie outside the byte taken
 #pragma unroll
-		for (int k = 0; k < 4; k++) r[k] >>= 2; // bits leaking across the half-words land in bytes 1 and 3, which are dropped
-		outw[0] = prmt(r[0], r[1], 0x6420);
-		outw[1] = prmt(r[2], r[3], 0x6420);
+			for (int k = 0; k < 4; k++) r[k] *= 64u;
+			outw[0] = prmt(r[0], r[1], 0x7531);
+			outw[1] = prmt(r[2], r[3], 0x7531);
+		} else {
+#pragma unroll
+			for (int k = 0; k < 4; k++) r[k] >>= 2; // bits leaking across the half-words land in bytes 1 and 3, which are dropped
+			outw[0] = prmt(r[0], r[1], 0x6420);
+			outw[1] = prmt(r[2], r[3], 0x6420);
+		}
 	} else {
 		outw[0] = r[0]; outw[1] = r[1]; outw[2] = r[2]; outw[3] = r[3];
 	}

@@ -2,9 +2,10 @@
 // single pattern slot (every AFGS1 config, most FGC-SEI configs), rows
 // aligned for 128-bit access, widths a multiple of 8 samples.
 //
-// Same decomposition as fgs_task.h (warp-task = 256 samples x the lines of one stripe, lane = 8
-// samples, neighbours' edge samples recomputed from their own LFSR window), but the per-sample work
-// is cut to the bone:
+// Same decomposition as fgs_task.h (warp-task = 32 lane units x the lines of one stripe, neighbours'
+// edge samples recomputed from their own LFSR window); a lane unit is 16 samples -- a whole 16-sample
+// block, one 256-bit access per line -- where width and alignment allow it (wide_task_body, the form
+// the usual picture sizes take), else 8 samples (fast_task_body). The per-sample work is cut to the bone:
 //   * with one pattern slot the unscaled grain does not depend on the sample, so a lane's 8 grain
 //     bytes per line are one contiguous octet of a pattern row: one 64-bit shared load (the image
 //     keeps column-shifted copies so that every window starts on an 8-byte boundary, and skews the

@@ -50,10 +50,10 @@ VFGS_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
 #endif
 }
 // sign-extended byte e (0..7) of the octet {w1,w0}. FMA_TOP: the top byte of each word comes out of a multiply-high
-// (arithmetic shift by 24 on the FMA pipe): the ALU pipe is the busier one in the issue-bound variants (8-bit output
-// or input: +0.3 / +5 points measured); the HBM-bound 16-bit variant loses 2 points with it and keeps the PRMT.
+// (arithmetic shift by 24 on the FMA pipe). Round 1 measured that ahead for the issue-bound variants under its burst
+// protocol; under the sustained protocol IMAD.HI is the expensive instruction and the PRMT wins, so it is off now.
 #ifndef VFGS_OCTET_TOP_ON_FMA
-#define VFGS_OCTET_TOP_ON_FMA 1 // build-time knob for experiments
+#define VFGS_OCTET_TOP_ON_FMA 0 // round 1: 1. Under the sustained protocol the multiply-high costs more than the PRMT it saves (profiles/r02_wide16_ab.md, trips 4-5)
 #endif
 template <int E, bool FMA_TOP = false>
 VFGS_HD int octet_byte(uint32_t w0, uint32_t w1)
@@ -487,7 +487,7 @@ VFGS_HD void scale_add_clip_8bit(smem_addr_t lut, uint32_t lo2, uint32_t hi2, co
 // constant and on the clip range (the callers pass lo + 2, hi + 2): clip(v + d, lo, hi) + 2 == clip(v + d + 2, lo + 2, hi + 2).
 // outw: 4 words (16-bit output) or 2 (8-bit).
 #ifndef VFGS_OUT8_MUL64
-#define VFGS_OUT8_MUL64 0 // build-time knob for experiments
+#define VFGS_OUT8_MUL64 1 // 10 -> 8: the >> 2 as a multiply (FMA pipe), +1 point with the PRMT top byte (profiles/r02_wide16_ab.md, trips 4-5)
 #endif
 template <bool OUT8>
 VFGS_HD void scale_add_clip_16bit(smem_addr_t lut, uint32_t lo2, uint32_t hi2, const int g[8], const uint32_t raw[4], uint32_t* outw)

@@ -130,6 +130,26 @@ def test_fast_path_garbage_samples_and_minus_128(emu):
     assert mask == 5 and np.array_equal(got, o.add_grain_frames(frames, n, w, h, 0))  # gather code, sign by multiplication
 
 
+def test_10_to_8_at_the_ceiling(emu):
+    """10 -> 8 bit output of samples at and above the 10-bit ceiling with the full range legal: the clip ceiling is
+    255 << 2 = 1020 (vfgs_hw.c:364-380), so (x + 2) >> 2 tops out at 255 and the uint8 cast of yuv.c:231 never wraps.
+    The kernels take the shift as byte 1 of (x + 2) * 64, which needs x + 2 < 1024 to stay inside its half-word."""
+    case = "fgs_afgs1_test1.cfg|d10|420|g100"
+    rng = np.random.default_rng(9)
+    for (w, h) in ((512, 40), (264, 34)):          # 16 and 8 samples per lane
+        n = w * h * 3 // 2
+        for kind in range(3):
+            if kind == 0: frames = rng.integers(1016, 1024, size=n, dtype=np.uint16)
+            elif kind == 1: frames = np.full(n, 1023, dtype=np.uint16)
+            else: frames = rng.choice(np.array([0, 3, 1019, 1022, 1023, 1024, 0x3fff, 0x4000, 0xffff], dtype=np.uint16), size=n)
+            o = Oracle(); program_case(o, G, case)
+            o.vfgs_set_legal_range(0)
+            got, mask = run_emu(emu, o, frames, 1, w, h, 8)
+            want = o.add_grain_frames(frames, 1, w, h, 8)
+            assert mask == 1 and np.array_equal(got, want), (w, h, kind, first_mismatch(got, want, w, h, "420", 1))
+            assert (want == 255).any() and want.max() == 255
+
+
 @pytest.mark.parametrize("w,h,n", [(144, 1, 2), (144, 15, 3), (136, 16, 2), (160, 17, 2), (130, 31, 1), (16384, 18, 1), (8200, 20, 1),
                                    (1366, 40, 2), (1928, 24, 1), (203, 30, 2), (366, 19, 3)])
 def test_extreme_geometries(emu, w, h, n):

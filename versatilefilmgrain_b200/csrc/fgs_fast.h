@@ -508,8 +508,8 @@ VFGS_HD void scale_add_clip_16bit(smem_addr_t lut, uint32_t lo2, uint32_t hi2, c
 	}
 	if (OUT8) {
 		if (VFGS_OUT8_MUL64) {
-			// (x >> 2) & 0xff is byte 1 of x * 64 (FMA pipe instead of ALU); x <= 1025, so a half-word can overflow by one bit
-			// into bit 0 of its neighbour, whose low six bits are zero (no carry) and lie outside the byte taken
+			// (x >> 2) & 0xff is byte 1 of x * 64 (FMA pipe instead of ALU); x <= hi + 2 <= (255 << 2) + 2 (the clip
+			// ceiling, vfgs_hw.c:364-380), so x * 64 stays inside its half-word
 #pragma unroll
 			for (int k = 0; k < 4; k++) r[k] *= 64u;
 			outw[0] = prmt(r[0], r[1], 0x7531);

@@ -136,7 +136,7 @@ def test_10_to_8_at_the_ceiling(emu):
     The kernels take the shift as byte 1 of (x + 2) * 64, which needs x + 2 < 1024 to stay inside its half-word."""
     case = "fgs_afgs1_test1.cfg|d10|420|g100"
     rng = np.random.default_rng(9)
-    for (w, h) in ((512, 40), (264, 34)):          # 16 and 8 samples per lane
+    for (w, h) in ((512, 40), (272, 34)):          # 16 samples per lane; 272: chroma rows of 136 samples take 8 per lane
         n = w * h * 3 // 2
         for kind in range(3):
             if kind == 0: frames = rng.integers(1016, 1024, size=n, dtype=np.uint16)
